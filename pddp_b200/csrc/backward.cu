@@ -1,0 +1,293 @@
+// Backward Riccati pass (ref: pddp/controllers/ilqr.py:489-674, default V_zz_reg=False branch;
+// pddp/utils/constraint.py:150-266 for the box-constrained feed-forward term, nu == 1).
+//
+// Two kernels, both sequential in time from t = N-1 down to 0 with V_z / V_zz resident on chip:
+//   * backward_thread_kernel<NZ>: one THREAD per problem, everything in registers; with the
+//     PDDP_BATCH_INNER layout every load/store is coalesced across problems.  Used for the
+//     small-state configs (pendulum nz=2, cartpole nz=4: the "backward-pass bandwidth study").
+//   * backward_warp_kernel: one WARP per problem, V_zz / F_z / V_zz.F_z in shared memory, lanes
+//     tile the nz x nz outputs; a problem's per-step record is contiguous (PDDP_PROBLEM_MAJOR) so
+//     the warp streams it with coalesced loads.  Used for nz = 14 (UT-Cholesky cartpole) and
+//     nz = 42 (full-covariance double cartpole).
+// Roofline: HBM -- per trajectory-step 2nz^2+2nz*nu+nz+nu+nu^2 elements read, nu+nu*nz written.
+#include "core.cuh"
+#include "kernels.h"
+
+namespace pddp {
+
+// scalar box-QP, a faithful restatement of the reference loop for a 1x1 problem.
+// returns the reference's result code; x = solution, is_free = (not clamped at exit),
+// qfree = Q (the "Cholesky factor squared" used for the feedback gain).
+template <class T>
+__device__ __forceinline__ int boxqp1(T x0, T Q, T c, T lo, T hi, T& x, bool& is_free) {
+    const T min_grad = T(1e-8), tol = T(1e-8), step_dec = T(0.6), min_step = T(1e-22), armijo = T(0.1);
+    x = clampv(x0, lo, hi);
+    if (isinf(x)) x = T(0);
+    T f = T(0.5) * x * Q * x + x * c;
+    int result = 0;
+    T old_f = T(0);
+    bool clamped = false;
+    is_free = true;
+    T chol = T(0);
+    for (int it = 0; it < 100; ++it) {
+        if (result != 0) break;
+        if (it > 0 && (old_f - f) < tol * fabs(old_f)) { result = 4; break; }
+        old_f = f;
+        T g = Q * x + c;
+        bool was = clamped;
+        clamped = (x == lo && g > T(0)) || (x == hi && g < T(0));
+        is_free = !clamped;
+        if (clamped) { result = 6; break; }
+        if (it == 0 || was != clamped) {
+            if (!(Q > T(0))) { result = -1; break; }
+            chol = jsqrt(Q);
+        }
+        if (fabs(g) < min_grad) { result = 5; break; }
+        T search = -((c / chol) / chol) - x;
+        T sdotg = search * g;
+        T step = T(1);
+        T xc = clampv(x + step * search, lo, hi);
+        T fc = T(0.5) * xc * Q * xc + xc * c;
+        while ((fc - old_f) / (step * sdotg) < armijo) {
+            step *= step_dec;
+            xc = clampv(x + step * search, lo, hi);
+            fc = T(0.5) * xc * Q * xc + xc * c;
+            if (step < min_step) { result = 2; break; }
+        }
+        x = xc;
+        f = fc;
+    }
+    return result;
+}
+
+// gains for nu == 1.  Returns false where the reference raises (-> NOT_PD).
+template <class T>
+__device__ __forceinline__ bool gains1(T Quu, T Qu, T reg, bool bounded, T lo, T hi, T warm, T& k,
+                                       T& inv /* K = -Q_uz * inv */) {
+    if (!isfinite(Quu)) return false;                    // linalg.eig raises on NaN/Inf
+    T e = Quu < T(0) ? T(1e-12) : Quu;                    // ref: ilqr.py:633
+    e += reg;
+    if (!bounded) {
+        inv = T(1) / e;
+        k = -inv * Qu;
+        return !(k != k);
+    }
+    bool is_free;
+    int result = boxqp1(warm, e, Qu, lo, hi, k, is_free);
+    if (result < 1) return false;
+    T ch = jsqrt(e);
+    inv = is_free ? (T(1) / ch) / ch : T(0);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+template <class T, int NZ>
+__global__ void __launch_bounds__(128) backward_thread_kernel(const BackwardArgs<T> a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    if (a.active && a.active[b] == 0) return;
+    const bool bounded = a.u_min != nullptr && a.u_max != nullptr;
+    const T reg = (T)a.mu[b];
+    T lo = T(0), hi = T(0);
+    if (bounded) { lo = a.u_min[0]; hi = a.u_max[0]; }
+    T v[NZ], V[NZ][NZ];
+#pragma unroll
+    for (int i = 0; i < NZ; ++i) {
+        v[i] = a.L_z[a.lLz.at(b, a.N, i)];
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) V[i][j] = a.L_zz[a.lLzz.at(b, a.N, i * NZ + j)];
+    }
+    T k_next = T(0);
+    bool ok = true;
+    for (int t = a.N - 1; t >= 0; --t) {
+        T Fz[NZ][NZ], Fu[NZ];
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) {
+            Fu[i] = a.F_u[a.lFu.at(b, t, i)];
+#pragma unroll
+            for (int j = 0; j < NZ; ++j) Fz[i][j] = a.F_z[a.lFz.at(b, t, i * NZ + j)];
+        }
+        T W[NZ][NZ], wu[NZ];                               // W = V Fz, wu = V Fu
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) {
+            T su = T(0);
+#pragma unroll
+            for (int kk = 0; kk < NZ; ++kk) su += V[i][kk] * Fu[kk];
+            wu[i] = su;
+#pragma unroll
+            for (int j = 0; j < NZ; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int kk = 0; kk < NZ; ++kk) s += V[i][kk] * Fz[kk][j];
+                W[i][j] = s;
+            }
+        }
+        T Qz[NZ], Quz[NZ], Qzz[NZ][NZ];
+        T Qu = a.L_u[a.lLu.at(b, t, 0)], Quu = a.L_uu[a.lLuu.at(b, t, 0)];
+#pragma unroll
+        for (int kk = 0; kk < NZ; ++kk) {
+            Qu += Fu[kk] * v[kk];
+            Quu += Fu[kk] * wu[kk];
+        }
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) {
+            T sz = a.L_z[a.lLz.at(b, t, i)], suz = a.L_uz[a.lLuz.at(b, t, i)];
+#pragma unroll
+            for (int kk = 0; kk < NZ; ++kk) {
+                sz += Fz[kk][i] * v[kk];
+                suz += Fu[kk] * W[kk][i];
+            }
+            Qz[i] = sz;
+            Quz[i] = suz;
+#pragma unroll
+            for (int j = 0; j < NZ; ++j) {
+                T s = a.L_zz[a.lLzz.at(b, t, i * NZ + j)];
+#pragma unroll
+                for (int kk = 0; kk < NZ; ++kk) s += Fz[kk][i] * W[kk][j];
+                Qzz[i][j] = s;
+            }
+        }
+        T kt, inv;
+        T ut = bounded ? a.U[a.lU.at(b, t, 0)] : T(0);
+        ok = gains1(Quu, Qu, reg, bounded, lo - ut, hi - ut, k_next, kt, inv);
+        T Kt[NZ];
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) {
+            Kt[i] = -Quz[i] * inv;
+            if (Kt[i] != Kt[i]) ok = false;
+        }
+        if (!ok) break;
+        k_next = kt;
+        a.k[a.lk.at(b, t, 0)] = kt;
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) a.K[a.lK.at(b, t, i)] = Kt[i];
+        // value update with the UN-regularised Q_uu (ref: ilqr.py:664-672)
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) v[i] = Qz[i] + Kt[i] * Qu + Kt[i] * Quu * kt + Quz[i] * kt;
+#pragma unroll
+        for (int i = 0; i < NZ; ++i)
+#pragma unroll
+            for (int j = 0; j < NZ; ++j)
+                V[i][j] = T(0.5) * (Qzz[i][j] + Qzz[j][i]) + Kt[i] * Quu * Kt[j] + Kt[i] * Quz[j] + Quz[i] * Kt[j];
+    }
+    a.status[b] = ok ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// warp per problem; dynamic smem: per warp 3*nz*nz + 6*nz elements
+template <class T>
+__global__ void __launch_bounds__(128) backward_warp_kernel(const BackwardArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int b = blockIdx.x * wpb + warp;
+    if (b >= a.B) return;
+    if (a.active && a.active[b] == 0) return;
+    const int nz = a.nz, nn = nz * nz;
+    T* base = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (3 * nn + 6 * nz);
+    T *V = base, *Fz = base + nn, *W = base + 2 * nn;
+    T *v = base + 3 * nn, *Fu = v + nz, *wu = Fu + nz, *Quz = wu + nz, *Qz = Quz + nz, *Kt = Qz + nz;
+    const bool bounded = a.u_min != nullptr && a.u_max != nullptr;
+    const T reg = (T)a.mu[b];
+    T lo = T(0), hi = T(0);
+    if (bounded) { lo = a.u_min[0]; hi = a.u_max[0]; }
+
+    for (int e = lane; e < nn; e += 32) V[e] = a.L_zz[a.lLzz.at(b, a.N, e)];
+    for (int e = lane; e < nz; e += 32) v[e] = a.L_z[a.lLz.at(b, a.N, e)];
+    __syncwarp();
+    T k_next = T(0);
+    bool ok = true;
+    for (int t = a.N - 1; t >= 0; --t) {
+        for (int e = lane; e < nn; e += 32) Fz[e] = a.F_z[a.lFz.at(b, t, e)];
+        for (int e = lane; e < nz; e += 32) Fu[e] = a.F_u[a.lFu.at(b, t, e)];
+        __syncwarp();
+        // W = V Fz ; wu = V Fu
+        for (int e = lane; e < nn; e += 32) {
+            const int i = e / nz, j = e - i * nz;
+            T s = T(0);
+            for (int kk = 0; kk < nz; ++kk) s += V[i * nz + kk] * Fz[kk * nz + j];
+            W[e] = s;
+        }
+        for (int i = lane; i < nz; i += 32) {
+            T s = T(0);
+            for (int kk = 0; kk < nz; ++kk) s += V[i * nz + kk] * Fu[kk];
+            wu[i] = s;
+        }
+        __syncwarp();
+        // Q_z, Q_uz (vectors), Q_u, Q_uu (scalars, every lane computes them redundantly)
+        for (int i = lane; i < nz; i += 32) {
+            T sz = a.L_z[a.lLz.at(b, t, i)], suz = a.L_uz[a.lLuz.at(b, t, i)];
+            for (int kk = 0; kk < nz; ++kk) {
+                sz += Fz[kk * nz + i] * v[kk];
+                suz += Fu[kk] * W[kk * nz + i];
+            }
+            Qz[i] = sz;
+            Quz[i] = suz;
+        }
+        T Qu = a.L_u[a.lLu.at(b, t, 0)], Quu = a.L_uu[a.lLuu.at(b, t, 0)];
+        for (int kk = 0; kk < nz; ++kk) {
+            Qu += Fu[kk] * v[kk];
+            Quu += Fu[kk] * wu[kk];
+        }
+        __syncwarp();
+        // Q_zz = L_zz + Fz^T W  -> overwrites V (V is dead once W and wu exist)
+        for (int e = lane; e < nn; e += 32) {
+            const int i = e / nz, j = e - i * nz;
+            T s = a.L_zz[a.lLzz.at(b, t, e)];
+            for (int kk = 0; kk < nz; ++kk) s += Fz[kk * nz + i] * W[kk * nz + j];
+            V[e] = s;
+        }
+        T kt, inv;
+        T ut = bounded ? a.U[a.lU.at(b, t, 0)] : T(0);
+        ok = gains1(Quu, Qu, reg, bounded, lo - ut, hi - ut, k_next, kt, inv);
+        bool bad = false;
+        for (int i = lane; i < nz; i += 32) {
+            T Ki = -Quz[i] * inv;
+            Kt[i] = Ki;
+            bad |= (Ki != Ki);
+        }
+        ok = ok && !__any_sync(0xffffffffu, bad);
+        if (!ok) break;
+        __syncwarp();
+        k_next = kt;
+        if (lane == 0) a.k[a.lk.at(b, t, 0)] = kt;
+        for (int i = lane; i < nz; i += 32) {
+            a.K[a.lK.at(b, t, i)] = Kt[i];
+            v[i] = Qz[i] + Kt[i] * Qu + Kt[i] * Quu * kt + Quz[i] * kt;
+        }
+        // symmetrise Q_zz and add the gain terms, one lane owns both (i,j) and (j,i)
+        for (int e = lane; e < nn; e += 32) {
+            const int i = e / nz, j = e - i * nz;
+            if (j < i) continue;
+            T q = T(0.5) * (V[i * nz + j] + V[j * nz + i]);
+            T val = q + Kt[i] * Quu * Kt[j] + Kt[i] * Quz[j] + Quz[i] * Kt[j];
+            V[i * nz + j] = val;
+            V[j * nz + i] = val;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) a.status[b] = ok ? 0 : 1;
+}
+
+template <class T>
+cudaError_t backward_pass(const BackwardArgs<T>& a, int layout, cudaStream_t s) {
+    const int threads = 128;
+    if (layout == LAYOUT_BATCH_INNER && (a.nz == 2 || a.nz == 4)) {
+        const int grid = (a.B + threads - 1) / threads;
+        if (a.nz == 2) backward_thread_kernel<T, 2><<<grid, threads, 0, s>>>(a);
+        else backward_thread_kernel<T, 4><<<grid, threads, 0, s>>>(a);
+        return cudaGetLastError();
+    }
+    const size_t per_warp = (size_t)(3 * a.nz * a.nz + 6 * a.nz) * sizeof(T);
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+    if (per_warp * wpb > 227 * 1024) return cudaErrorInvalidValue;
+    const size_t smem = per_warp * wpb;
+    cudaError_t e = cudaFuncSetAttribute(backward_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    backward_warp_kernel<T><<<(a.B + wpb - 1) / wpb, wpb * 32, smem, s>>>(a);
+    return cudaGetLastError();
+}
+template cudaError_t backward_pass<float>(const BackwardArgs<float>&, int, cudaStream_t);
+template cudaError_t backward_pass<double>(const BackwardArgs<double>&, int, cudaStream_t);
+
+}  // namespace pddp

@@ -1,0 +1,175 @@
+// Per-problem controller state machine (accept / reject / regularisation schedule) and the
+// stand-alone cost linearisation used by the BNN path.
+#include "core.cuh"
+#include "kernels.h"
+
+namespace pddp {
+
+// ref: pddp/controllers/ilqr.py:364-390 (Tassa schedule, python floats -> doubles here)
+__device__ __forceinline__ bool increase_reg(double& mu, double& delta, double max_reg) {
+    delta = fmax(1.0, delta) * 2.0;
+    mu = fmax(1e-6, mu * delta);
+    return mu < max_reg;
+}
+__device__ __forceinline__ void decrease_reg(double& mu, double& delta) {
+    delta = fmin(1.0, delta) / 2.0;
+    mu *= delta;
+    if (mu <= 1e-6) mu = 0.0;
+}
+
+// ref: pddp/controllers/ilqr.py:140-181 (tail of _step), one thread per problem.
+// active[b]: 0 finished, 1 needs a fresh linearisation, 2 retry backward+rollout on the old one.
+template <class T>
+__global__ void accept_state_kernel(const AcceptArgs<T> a, int32_t* accepted) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    accepted[b] = 0;
+    if (a.active[b] == 0) return;
+    double mu = a.mu[b], delta = a.delta[b];
+    int state;
+    if (a.bw_status && a.bw_status[b] != 0) {
+        state = increase_reg(mu, delta, a.max_reg) ? ST_NOT_PD : ST_MAX_REG;
+    } else {
+        const T Jn = a.J_new[b], Jo = a.J_opt[b];
+        if (Jn < Jo) {
+            accepted[b] = 1;
+            decrease_reg(mu, delta);
+            T change = fabs(Jo - Jn) / Jo;
+            state = change < (T)a.tol ? ST_CONVERGED : ST_ACCEPTED;
+            a.J_opt[b] = Jn;
+        } else {
+            state = increase_reg(mu, delta, a.max_reg) ? ST_REJECTED : ST_MAX_REG;
+        }
+    }
+    a.mu[b] = mu;
+    a.delta[b] = delta;
+    a.state[b] = state;
+    int act;
+    if (state == ST_CONVERGED || state == ST_MAX_REG) act = 0;
+    else if (state == ST_ACCEPTED) {
+        int left = a.iters_left[b] - 1;
+        a.iters_left[b] = left;
+        act = left > 0 ? 1 : 0;
+    } else act = 2;
+    a.active[b] = act;
+    if (act != 0 && a.n_active) atomicAdd(a.n_active, 1);
+}
+
+// copy the accepted candidates into the nominal trajectory (self._Z_nominal/_U_nominal)
+template <class T>
+__global__ void accept_copy_kernel(const AcceptArgs<T> a, const int32_t* accepted) {
+    const int64_t per = (int64_t)(a.N + 1) * a.nz + (int64_t)a.N * a.nu;
+    const int64_t total = per * a.B;
+    for (int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; id < total;
+         id += (int64_t)gridDim.x * blockDim.x) {
+        // id enumerates (slot, b) with b fastest for BATCH_INNER-friendly coalescing; for
+        // PROBLEM_MAJOR the layout strides make consecutive slots contiguous instead.
+        int64_t b, slot;
+        if (a.lZ.sb == 1) { b = id % a.B; slot = id / a.B; }
+        else { b = id / per; slot = id % per; }
+        if (!accepted[b]) continue;
+        if (slot < (int64_t)(a.N + 1) * a.nz) {
+            int64_t t = slot / a.nz, e = slot % a.nz;
+            a.Z[a.lZ.at(b, t, e)] = a.Z_new[a.lZ.at(b, t, e)];
+        } else {
+            slot -= (int64_t)(a.N + 1) * a.nz;
+            int64_t t = slot / a.nu, e = slot % a.nu;
+            a.U[a.lU.at(b, t, e)] = a.U_new[a.lU.at(b, t, e)];
+        }
+    }
+}
+
+template <class T>
+cudaError_t accept_update(const AcceptArgs<T>& a, int32_t* accepted_scratch, cudaStream_t s) {
+    accept_state_kernel<T><<<(a.B + 127) / 128, 128, 0, s>>>(a, accepted_scratch);
+    const int64_t total = ((int64_t)(a.N + 1) * a.nz + (int64_t)a.N * a.nu) * a.B;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    accept_copy_kernel<T><<<grid, 256, 0, s>>>(a, accepted_scratch);
+    return cudaGetLastError();
+}
+template cudaError_t accept_update<float>(const AcceptArgs<float>&, int32_t*, cudaStream_t);
+template cudaError_t accept_update<double>(const AcceptArgs<double>&, int32_t*, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone cost linearisation: one thread per (problem, time, Hessian pair).
+// Replaces batch_eval_cost (pddp/utils/evaluation.py:134-239) for a whole nominal trajectory.
+// ------------------------------------------------------------------------------------------
+template <class T, int GEO, int ENC>
+__global__ void __launch_bounds__(128) cost_pairs_kernel(const CostDerivArgs<T> a) {
+    typedef Geo<GEO> G;
+    constexpr int D = G::D, NZ = enc_size(D, ENC), NP = NZ * (NZ + 1) / 2;
+    const int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t site = id / NP;
+    if (site >= (int64_t)a.B * (a.N + 1)) return;
+    int p = (int)(id - site * NP);
+    const int b = (int)(site / (a.N + 1)), t = (int)(site - (int64_t)b * (a.N + 1));
+    if (a.active && a.active[b] != 1) return;
+    int i = 0;
+    while (p >= NZ - i) { p -= NZ - i; ++i; }
+    const int j = i + p;
+    typedef Jet2<T, 2> S;
+    S zj[NZ];
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) {
+        zj[k] = S(a.Z[a.lZ.at(b, t, k)]);
+        zj[k].g[0] = k == i ? T(1) : T(0);
+        zj[k].g[1] = k == j ? T(1) : T(0);
+    }
+    const bool terminal = t == a.N;
+    S r = cost_state<GEO, ENC, T, S>(a.cost, zj, terminal);
+    a.L_zz[a.lLzz.at(b, t, i * NZ + j)] = r.h[1];
+    if (i != j) a.L_zz[a.lLzz.at(b, t, j * NZ + i)] = r.h[1];
+    else a.L_z[a.lLz.at(b, t, i)] = r.g[0];
+    if (i == 0) a.L_uz && !terminal ? (void)(a.L_uz[a.lLuz.at(b, t, j)] = T(0)) : (void)0;
+    if (i == 0 && j == 0) {
+        T l = r.v;
+        if (!terminal) {
+            T la, lu, luu;
+            cost_action(a.cost, a.U[a.lU.at(b, t, 0)], la, lu, luu);
+            l += la;
+            a.L_u[a.lLu.at(b, t, 0)] = lu;
+            a.L_uu[a.lLuu.at(b, t, 0)] = luu;
+        }
+        a.L[a.lL.at(b, t, 0)] = l;
+    }
+}
+
+template <class T>
+__global__ void cost_sum_kernel(const CostDerivArgs<T> a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    if (a.active && a.active[b] != 1) return;
+    T J = T(0);
+    for (int t = 0; t <= a.N; ++t) J += a.L[a.lL.at(b, t, 0)];
+    a.J_opt[b] = J;
+}
+
+template <class T, int GEO, int ENC>
+static cudaError_t launch_cost(const CostDerivArgs<T>& a, cudaStream_t s) {
+    constexpr int NZ = enc_size(Geo<GEO>::D, ENC), NP = NZ * (NZ + 1) / 2;
+    const int64_t total = (int64_t)a.B * (a.N + 1) * NP;
+    cost_pairs_kernel<T, GEO, ENC><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a);
+    if (a.J_opt) cost_sum_kernel<T><<<(a.B + 127) / 128, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <class T>
+cudaError_t cost_derivatives(int geo, int enc, const CostDerivArgs<T>& a, cudaStream_t s) {
+    switch (geo * 8 + enc) {
+        case GEO_PENDULUM * 8 + ENC_FULL: return launch_cost<T, GEO_PENDULUM, ENC_FULL>(a, s);
+        case GEO_PENDULUM * 8 + ENC_UT: return launch_cost<T, GEO_PENDULUM, ENC_UT>(a, s);
+        case GEO_PENDULUM * 8 + ENC_IGNORE: return launch_cost<T, GEO_PENDULUM, ENC_IGNORE>(a, s);
+        case GEO_CARTPOLE * 8 + ENC_FULL: return launch_cost<T, GEO_CARTPOLE, ENC_FULL>(a, s);
+        case GEO_CARTPOLE * 8 + ENC_UT: return launch_cost<T, GEO_CARTPOLE, ENC_UT>(a, s);
+        case GEO_CARTPOLE * 8 + ENC_IGNORE: return launch_cost<T, GEO_CARTPOLE, ENC_IGNORE>(a, s);
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_FULL: return launch_cost<T, GEO_DOUBLE_CARTPOLE, ENC_FULL>(a, s);
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_UT: return launch_cost<T, GEO_DOUBLE_CARTPOLE, ENC_UT>(a, s);
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_IGNORE: return launch_cost<T, GEO_DOUBLE_CARTPOLE, ENC_IGNORE>(a, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+template cudaError_t cost_derivatives<float>(int, int, const CostDerivArgs<float>&, cudaStream_t);
+template cudaError_t cost_derivatives<double>(int, int, const CostDerivArgs<double>&, cudaStream_t);
+
+}  // namespace pddp

@@ -1,0 +1,264 @@
+"""Batched iLQR / PDDP iteration on the GPU: B independent problems advance together, one pass =
+linearise -> backward Riccati -> rollout with parallel line search -> per-problem accept/reject.
+
+This is the host side of the hot path: it owns the device buffers (laid out once, reused by every
+pass), marshals pointers into the C ABI and never touches the data itself.  There is no CPU path.
+
+ref: pddp/controllers/ilqr.py:102-316 (what one problem's `step`/`fit` do; here vectorised over B
+with per-problem mu/delta/state, SURVEY.md section 5 "failure detection" row).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .encoding import StateEncoding, infer_encoded_state_size
+
+LIN_NAMES = ("Z", "F_z", "F_u", "L", "L_z", "L_u", "L_zz", "L_uz", "L_uu")
+
+
+def fit_alphas(dtype=torch.float32, device=None, n=10):
+    """Line-search candidates of `fit`: 1.025 ** -(j^2), j < n.  ref: pddp/controllers/ilqr.py:282"""
+    return (1.025 ** (-torch.arange(float(n), dtype=torch.float64) ** 2)).to(dtype=dtype,
+                                                                             device=device)
+
+
+def step_alphas(dtype=torch.float32, device=None):
+    """Default candidates of `step` / MPC: 10 ** linspace(0,-3,11).  ref: ilqr.py:189"""
+    return (10.0 ** torch.linspace(0, -3, 11, dtype=torch.float64)).to(dtype=dtype, device=device)
+
+
+class KnownDynamics:
+    """Closed-form dynamics constants (ref: pddp/examples/<problem>/model.py constructors)."""
+
+    def __init__(self, geo, params):
+        self.geo = geo
+        self.params = [float(p) for p in params]
+        self.is_bnn = False
+
+    def c_struct(self):
+        s = _lib.KnownDynamics()
+        for i, p in enumerate(self.params):
+            s.p[i] = p
+        return s
+
+
+class QRCostConstants:
+    """Q, R, Q_term, x_goal, u_goal of a QRCost on the augmented state (ref: costs/quadratic.py)."""
+
+    def __init__(self, Q, R, Q_term, x_goal, u_goal=None):
+        self.Q = torch.as_tensor(Q, dtype=torch.float64).cpu()
+        self.Q_term = torch.as_tensor(Q_term, dtype=torch.float64).cpu()
+        self.R = torch.as_tensor(R, dtype=torch.float64).cpu().reshape(-1)
+        self.x_goal = torch.as_tensor(x_goal, dtype=torch.float64).cpu().reshape(-1)
+        ug = torch.zeros(1, dtype=torch.float64) if u_goal is None else torch.as_tensor(
+            u_goal, dtype=torch.float64).cpu().reshape(-1)
+        self.u_goal = ug
+
+    def c_struct(self):
+        DA = self.Q.shape[0]
+        if DA > _lib.MAX_DA or self.Q.shape != (DA, DA) or self.Q_term.shape != (DA, DA):
+            raise ValueError("Q / Q_term must be square, at most %dx%d" % (_lib.MAX_DA, _lib.MAX_DA))
+        if self.R.numel() != 1:
+            raise NotImplementedError("pddp_b200: only action_size == 1 is implemented")
+        s = _lib.Cost()
+        for i, v in enumerate(self.Q.reshape(-1).tolist()):
+            s.Q[i] = v
+        for i, v in enumerate(self.Q_term.reshape(-1).tolist()):
+            s.Q_term[i] = v
+        for i, v in enumerate(self.x_goal.tolist()):
+            s.x_goal[i] = v
+        s.R[0] = float(self.R[0])
+        s.u_goal[0] = float(self.u_goal.reshape(-1)[0])
+        return s
+
+
+class BatchedSolver:
+    """Device buffers + pass sequencing for B problems of one (dynamics, cost, encoding, N)."""
+
+    def __init__(self, dynamics, cost, encoding, B, N, dtype=torch.float32, device="cuda",
+                 layout=None, max_alphas=16):
+        self.lib = _lib.load()
+        self.dyn, self.cost = dynamics, cost
+        self.enc = StateEncoding(int(encoding))
+        self.geo = dynamics.geo
+        self.D, self.nu, _, _ = _lib.GEO_INFO[self.geo]
+        self.nz = infer_encoded_state_size(self.D, self.enc)
+        self.B, self.N, self.dtype = int(B), int(N), dtype
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("pddp_b200 runs on CUDA devices only (no CPU fallback)")
+        if layout is None:   # SoA for thread-per-problem kernels, records for warp-per-problem
+            layout = _lib.BATCH_INNER if (not dynamics.is_bnn and self.nz <= 6) else _lib.PROBLEM_MAJOR
+        self.layout = layout
+        self.shape = _lib.Shape(_lib.dtype_code(dtype), layout, self.geo, int(self.enc), self.B,
+                                self.N, self.nz, self.nu)
+        self.c_cost = cost.c_struct()
+        self.c_dyn = dynamics.c_struct() if not dynamics.is_bnn else None
+        nz, nu, N = self.nz, self.nu, self.N
+        dims = dict(Z=(N + 1, nz), F_z=(N, nz * nz), F_u=(N, nz * nu), L=(N + 1, 1), L_z=(N + 1, nz),
+                    L_u=(N, nu), L_zz=(N + 1, nz * nz), L_uz=(N, nu * nz), L_uu=(N, nu * nu),
+                    U=(N, nu), k=(N, nu), K=(N, nu * nz), Z_new=(N + 1, nz), U_new=(N, nu))
+        self.buf = {n: self._alloc(nt, e) for n, (nt, e) in dims.items()}
+        o = dict(device=self.device)
+        self.z0 = torch.zeros(self.B, nz, dtype=dtype, **o)
+        self.J_opt = torch.zeros(self.B, dtype=dtype, **o)
+        self.J_new = torch.zeros(self.B, dtype=dtype, **o)
+        self.max_alphas = int(max_alphas)
+        self.J_all = torch.zeros(self.B, 10, dtype=dtype, **o)
+        self.amin = torch.zeros(self.B, dtype=torch.int32, **o)
+        self.mu = torch.zeros(self.B, dtype=torch.float64, **o)
+        self.delta = torch.full((self.B,), 2.0, dtype=torch.float64, **o)
+        self.state = torch.zeros(self.B, dtype=torch.int32, **o)
+        self.iters_left = torch.zeros(self.B, dtype=torch.int32, **o)
+        self.active = torch.ones(self.B, dtype=torch.int32, **o)
+        self.accepted = torch.zeros(self.B, dtype=torch.int32, **o)
+        self.lin_status = torch.zeros(self.B, dtype=torch.int32, **o)
+        self.bw_status = torch.zeros(self.B, dtype=torch.int32, **o)
+        self.roll_status = torch.zeros(self.B, dtype=torch.int32, **o)
+        self.n_active = torch.zeros(1, dtype=torch.int32, **o)
+        self.u_min = self.u_max = None
+        self.alphas = fit_alphas(dtype, self.device)
+        self.launches = 0          # CUDA kernels enqueued by this solver (bench.py reports it)
+        self.workspace = None
+        if dynamics.is_bnn:
+            self.c_bnn = dynamics.c_struct(dtype, self.device)
+            nbytes = self.lib.pddp_bnn_workspace_bytes(C.byref(self.shape), C.byref(self.c_bnn),
+                                                       max_alphas)
+            if nbytes < 0:
+                _lib.check(int(nbytes), "bnn_workspace_bytes")
+            self.workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+
+    # ---------------------------------------------------------------- buffers
+    def _alloc(self, nt, e):
+        shape = (nt, e, self.B) if self.layout == _lib.BATCH_INNER else (self.B, nt, e)
+        return torch.zeros(shape, dtype=self.dtype, device=self.device)
+
+    def view(self, name):
+        """[B, Nt, E] view of a buffer whatever the internal layout."""
+        t = self.buf[name]
+        return t.permute(2, 0, 1) if self.layout == _lib.BATCH_INNER else t
+
+    def store(self, name, value):
+        """Copies a [B, Nt, E]-shaped tensor into the named buffer."""
+        self.view(name).copy_(value.reshape(self.view(name).shape))
+
+    def matrices(self, name):
+        """Reference-shaped view: F_z [B,N,nz,nz], K [B,N,nu,nz], L [B,N+1] ..."""
+        v = self.view(name)
+        nz, nu = self.nz, self.nu
+        shapes = dict(F_z=(nz, nz), F_u=(nz, nu), L_zz=(nz, nz), L_uz=(nu, nz), L_uu=(nu, nu),
+                      K=(nu, nz))
+        if name in shapes:
+            return v.reshape(v.shape[0], v.shape[1], *shapes[name])
+        if name == "L":
+            return v.reshape(v.shape[0], v.shape[1])
+        return v
+
+    # ---------------------------------------------------------------- setup
+    def set_problem(self, z0, U, u_min=None, u_max=None, alphas=None, iterations=1):
+        z0 = torch.as_tensor(z0)
+        _lib.require_cuda(z0, "z0")
+        self.z0.copy_(z0.reshape(self.B, self.nz))
+        self.store("U", torch.as_tensor(U))
+        if (u_min is None) != (u_max is None):
+            raise ValueError("u_min and u_max must be given together")
+        self.u_min = None if u_min is None else torch.as_tensor(u_min, dtype=self.dtype).reshape(
+            -1).to(self.device).contiguous()
+        self.u_max = None if u_max is None else torch.as_tensor(u_max, dtype=self.dtype).reshape(
+            -1).to(self.device).contiguous()
+        if alphas is not None:
+            self.alphas = torch.as_tensor(alphas).to(dtype=self.dtype, device=self.device).contiguous()
+        if self.alphas.numel() > self.max_alphas:
+            raise ValueError("more line-search candidates than max_alphas=%d" % self.max_alphas)
+        if self.alphas.numel() != self.J_all.shape[1]:     # the C ABI writes J_all as [B, A]
+            self.J_all = torch.zeros(self.B, self.alphas.numel(), dtype=self.dtype, device=self.device)
+        self.reset(iterations)
+
+    def reset(self, iterations=1):
+        """ref: ilqr.py:364-367 (_reset_reg) per problem + bookkeeping for `iterations` steps."""
+        self.mu.zero_()
+        self.delta.fill_(2.0)
+        self.state.zero_()
+        self.iters_left.fill_(int(iterations))
+        self.active.fill_(1)
+
+    # ---------------------------------------------------------------- the four stages
+    def linearize(self, use_active=True):
+        b, p = self.buf, _lib.ptr
+        act = p(self.active) if use_active else None
+        self.lin_status.zero_()
+        if self.dyn.is_bnn:
+            code = self.lib.pddp_linearize_bnn(
+                C.byref(self.shape), C.byref(self.c_bnn), C.byref(self.c_cost), p(self.z0), p(b["U"]),
+                p(self.u_min), p(self.u_max), act, *[p(b[n]) for n in LIN_NAMES], p(self.J_opt),
+                p(self.lin_status), p(self.workspace), self.workspace.numel(), _lib.stream_ptr())
+            _lib.check(code, "linearize_bnn")
+        else:
+            code = self.lib.pddp_linearize_known(
+                C.byref(self.shape), C.byref(self.c_dyn), C.byref(self.c_cost), p(self.z0), p(b["U"]),
+                p(self.u_min), p(self.u_max), act, *[p(b[n]) for n in LIN_NAMES], p(self.J_opt),
+                p(self.lin_status), _lib.stream_ptr())
+            _lib.check(code, "linearize_known")
+
+    def backward(self, use_active=True):
+        b, p = self.buf, _lib.ptr
+        code = self.lib.pddp_backward(
+            C.byref(self.shape), p(b["F_z"]), p(b["F_u"]), p(b["L_z"]), p(b["L_u"]), p(b["L_zz"]),
+            p(b["L_uz"]), p(b["L_uu"]), p(self.mu), p(b["U"]), p(self.u_min), p(self.u_max),
+            p(self.active) if use_active else None, p(b["k"]), p(b["K"]), p(self.bw_status),
+            _lib.stream_ptr())
+        _lib.check(code, "backward")
+
+    def rollout(self, use_active=True, use_bw_status=True):
+        b, p = self.buf, _lib.ptr
+        A = int(self.alphas.numel())
+        common = (p(b["Z"]), p(b["U"]), p(b["k"]), p(b["K"]), p(self.alphas), A, p(self.u_min),
+                  p(self.u_max), p(self.active) if use_active else None,
+                  p(self.bw_status) if use_bw_status else None, p(self.J_all), p(self.amin),
+                  p(self.J_new), p(b["Z_new"]), p(b["U_new"]))
+        if self.dyn.is_bnn:
+            code = self.lib.pddp_rollout_bnn(
+                C.byref(self.shape), C.byref(self.c_bnn), C.byref(self.c_cost), *common,
+                p(self.roll_status), p(self.workspace), self.workspace.numel(), _lib.stream_ptr())
+            _lib.check(code, "rollout_bnn")
+        else:
+            code = self.lib.pddp_rollout_known(C.byref(self.shape), C.byref(self.c_dyn),
+                                               C.byref(self.c_cost), *common, _lib.stream_ptr())
+            _lib.check(code, "rollout_known")
+
+    def accept(self, tol=5e-6, max_reg=1e10):
+        b, p = self.buf, _lib.ptr
+        self.n_active.zero_()
+        code = self.lib.pddp_accept_update(
+            C.byref(self.shape), p(self.J_new), p(self.bw_status), p(b["Z_new"]), p(b["U_new"]),
+            float(tol), float(max_reg), p(self.mu), p(self.delta), p(self.J_opt), p(self.state),
+            p(self.iters_left), p(self.active), p(b["Z"]), p(b["U"]), p(self.accepted),
+            p(self.n_active), _lib.stream_ptr())
+        _lib.check(code, "accept_update")
+
+    def iterate(self, tol=5e-6, max_reg=1e10):
+        """One pass of the hot path over the whole batch (no host synchronisation)."""
+        self.linearize()
+        self.backward()
+        self.rollout()
+        self.accept(tol, max_reg)
+
+    # ---------------------------------------------------------------- driver
+    def fit(self, z0, U, n_iterations=50, tol=5e-6, max_reg=1e10, u_min=None, u_max=None,
+            alphas=None, max_passes=None, on_pass=None):
+        """Runs every problem until it has done `n_iterations` accepted steps or reached a
+        terminal state (CONVERGED / MAX_REG), exactly like B sequential reference `fit` calls
+        (ref: ilqr.py:237-316); rejected / not-PD attempts retry with a larger mu and do not
+        consume iterations (ref: ilqr.py:213)."""
+        self.set_problem(z0, U, u_min, u_max, alphas, iterations=n_iterations)
+        passes = 0
+        limit = max_passes if max_passes is not None else n_iterations * 64
+        while passes < limit:
+            self.iterate(tol, max_reg)
+            passes += 1
+            if on_pass is not None:
+                on_pass(passes, self)
+            if int(self.n_active.item()) == 0:     # one 4-byte D2H read per pass
+                break
+        return self.view("Z"), self.view("U"), self.state

@@ -1,5 +1,650 @@
-// placeholder until the BNN kernels land
+// BNN (MC-dropout particle) dynamics: linearisation and line-search rollout.
+//
+// ref: pddp/models/bnn/modules.py:287-386 (BNNDynamicsModel.forward) + 200-264 (particle MLP),
+//      pddp/utils/particles.py:136-149, pddp/utils/encoding.py (moment matching back to z),
+//      pddp/controllers/ilqr.py:393-486 (forward), 677-723 (_control_law), 764-791 (cost).
+//
+// Time is sequential; every step is two launches over ALL problems:
+//   (1) the particle MLP (bnn_mlp_*): rows = problems x particles x (1 + tangents)   [tensor roofline]
+//   (2) a moment-matching kernel: mean / covariance / Cholesky of the new particles and -- in the
+//       linearise pass -- their forward-mode tangents w.r.t. every encoded input, chained through
+//       X_p = m + eps_p U with eps_p = (X_p - m) U^-1 held constant.
+// Particles are carried from step to step in the workspace; eps_in[0] and the dropout masks are
+// data supplied by the caller, so there is no RNG on this path.
 #include "../../include/pddp_b200.h"
-extern "C" int64_t pddp_bnn_workspace_bytes(const pddp_shape*, const pddp_bnn*, int32_t) { return PDDP_E_UNSUPPORTED; }
-extern "C" int pddp_linearize_bnn(const pddp_shape*, const pddp_bnn*, const pddp_cost*, const void*, const void*, const void*, const void*, const int32_t*, void*, void*, void*, void*, void*, void*, void*, void*, void*, void*, int32_t*, void*, int64_t, void*) { return PDDP_E_UNSUPPORTED; }
-extern "C" int pddp_rollout_bnn(const pddp_shape*, const pddp_bnn*, const pddp_cost*, const void*, const void*, const void*, const void*, const void*, int32_t, const void*, const void*, const int32_t*, const int32_t*, void*, int32_t*, void*, void*, void*, int32_t*, void*, int64_t, void*) { return PDDP_E_UNSUPPORTED; }
+#include "bnn_common.cuh"
+#include "bnn_mlp_simt.cuh"
+#include "kernels.h"
+#include <stdio.h>
+
+namespace pddp {
+
+// ------------------------------------------------------------------------------------------
+// weight prep: torch [out,in] -> [in,out] copies in the workspace (coalesced over outputs)
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void bnn_transpose_kernel(const T* W, int out, int in, int out_used, T* WT) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < in * out_used; i += gridDim.x * blockDim.x) {
+        const int k = i / out_used, o = i - k * out_used;
+        WT[i] = W[(size_t)o * in + k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// particles of step 0: X_p = m + eps0_p U(z0), one thread per (group s, particle p)
+// ------------------------------------------------------------------------------------------
+template <class T, int GEO, int ENC>
+__global__ void bnn_init_particles_kernel(const T* z, Layout lz, int groups_per_problem, long long S, int P,
+                                          const T* eps0, T* X, int32_t* status) {
+    constexpr int D = Geo<GEO>::D, NZ = enc_size(D, ENC);
+    const long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (id >= S * P) return;
+    const long long s = id / P;
+    const int p = (int)(id - s * P);
+    const int b = (int)(s / groups_per_problem);
+    T zz[NZ];
+#pragma unroll
+    for (int e = 0; e < NZ; ++e) zz[e] = z[lz.at(b, 0, e)];
+    T U[D][D];
+    if (!load_factor<D, ENC, T>(zz, U) && status) status[b] |= 2;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        T v = zz[c];
+#pragma unroll
+        for (int r = 0; r <= c; ++r) v += eps0[p * D + r] * U[r][c];
+        X[id * D + c] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// linearise: moment matching + Jacobian of one step, one warp per problem
+// ------------------------------------------------------------------------------------------
+template <class T>
+struct MomentLinArgs {
+    int B, N, t, P;
+    const T* X; const T* Xn; const T* Jp;       // [B,P,D], [B,P,D], [B,P,D,D+nu]
+    const int32_t* active;
+    T* Z; T* F_z; T* F_u; int32_t* status;
+    Layout lZ, lFz, lFu;
+};
+
+template <class T, int GEO, int ENC>
+__global__ void __launch_bounds__(128) bnn_moment_lin_kernel(const MomentLinArgs<T> a) {
+    typedef Geo<GEO> G;
+    constexpr int D = G::D, NU = G::NU, NZ = enc_size(D, ENC), TD = D + NU, NT = D * (D + 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int b = blockIdx.x * wpb + warp;
+    if (b >= a.B) return;
+    if (a.active && a.active[b] != 1) return;
+    const int P = a.P, t = a.t;
+    const int per = P * (3 * D + D * D);
+    T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)warp * per;
+    T *s_eps = sm, *s_xc = sm + P * D, *s_H = sm + 2 * P * D, *s_G = sm + 3 * P * D;   // eps, X'-M', dX'/du, dX'/dX
+
+    T z[NZ];
+#pragma unroll
+    for (int e = 0; e < NZ; ++e) z[e] = a.Z[a.lZ.at(b, t, e)];
+    T U[D][D];
+    bool ok = load_factor<D, ENC, T>(z, U);
+
+    // particles: eps = (X - m) U^-1 ; stage X', J ; partial sums for the mean
+    T msum[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) msum[d] = T(0);
+    for (int p = lane; p < P; p += 32) {
+        const size_t g = (size_t)b * P + p;
+        T delta[D], eps[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) delta[d] = a.X[g * D + d] - z[d];
+        solve_right_upper<D, T>(U, delta, eps);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            s_eps[p * D + d] = eps[d];
+            T xn = a.Xn[g * D + d];
+            s_xc[p * D + d] = xn;
+            msum[d] += xn;
+#pragma unroll
+            for (int c = 0; c < TD; ++c) {
+                T j = a.Jp[(g * D + d) * TD + c];
+                if (c < D) s_G[(p * D + d) * D + c] = j; else s_H[p * D + d] = j;
+            }
+        }
+    }
+    T M[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) M[d] = warp_sum(msum[d]) / T(P);
+    T csum[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) csum[i] = T(0);
+    for (int p = lane; p < P; p += 32) {
+        T xc[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) { xc[d] = s_xc[p * D + d] - M[d]; s_xc[p * D + d] = xc[d]; }
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int c = r; c < D; ++c) csum[tri<D>(r, c)] += xc[r] * xc[c];
+    }
+    T Cov[D][D];
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = r; c < D; ++c) {
+            T v = warp_sum(csum[tri<D>(r, c)]) / T(P - 1);    // ref: utils/particles.py:136-149
+            Cov[r][c] = v;
+            Cov[c][r] = v;
+        }
+    __syncwarp();
+    T zn[NZ], Un[D][D];
+    ok = encode_moments<D, ENC, T>(M, Cov, zn, Un) && ok;
+#pragma unroll
+    for (int e = 0; e < NZ; ++e)
+        if ((e & 31) == lane) a.Z[a.lZ.at(b, t + 1, e)] = zn[e];
+    if (lane == 0 && !ok && a.status) a.status[b] |= 2;
+
+    // one lane per input direction j in [z (NZ), u (NU)]
+    for (int j = lane; j < NZ + NU; j += 32) {
+        T dm[D], dUd[D][D], du = T(0);
+#pragma unroll
+        for (int d = 0; d < D; ++d) dm[d] = (j == d) ? T(1) : T(0);
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int c = 0; c < D; ++c) dUd[r][c] = T(0);
+        if (j >= NZ) du = T(1);
+        else if (j >= D) {
+            if (ENC == ENC_UT) {
+#pragma unroll
+                for (int r = 0; r < D; ++r)
+#pragma unroll
+                    for (int c = r; c < D; ++c) dUd[r][c] = (j - D == tri<D>(r, c)) ? T(1) : T(0);
+            } else if (ENC == ENC_FULL) {
+                // symmetrised direction (E_ab + E_ba)/2 through the Cholesky differential
+                T S[D][D];
+                const int ja = (j - D) / D, jb = (j - D) - ja * D;
+#pragma unroll
+                for (int r = 0; r < D; ++r)
+#pragma unroll
+                    for (int c = 0; c < D; ++c)
+                        S[r][c] = ((r == ja && c == jb) ? T(0.5) : T(0)) + ((r == jb && c == ja) ? T(0.5) : T(0));
+                chol_upper_diff<D, T>(U, S, dUd);
+            }
+        }
+        T dM[D], S2[D][D];
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            dM[r] = T(0);
+#pragma unroll
+            for (int c = 0; c < D; ++c) S2[r][c] = T(0);
+        }
+        for (int p = 0; p < P; ++p) {
+            T dx[D], dxn[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                T v = dm[c];
+                if (ENC != ENC_IGNORE) {
+#pragma unroll
+                    for (int r = 0; r <= c; ++r) v += s_eps[p * D + r] * dUd[r][c];
+                }
+                dx[c] = v;
+            }
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                T v = s_H[p * D + r] * du;
+#pragma unroll
+                for (int c = 0; c < D; ++c) v += s_G[(p * D + r) * D + c] * dx[c];
+                dxn[r] = v;
+                dM[r] += v;
+            }
+            if (ENC != ENC_IGNORE) {
+#pragma unroll
+                for (int r = 0; r < D; ++r)
+#pragma unroll
+                    for (int c = 0; c < D; ++c) S2[r][c] += dxn[r] * s_xc[p * D + c];
+            }
+        }
+        T col[NZ];
+#pragma unroll
+        for (int r = 0; r < D; ++r) col[r] = dM[r] / T(P);
+        if (ENC != ENC_IGNORE) {
+            T dC[D][D];
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+                for (int c = 0; c < D; ++c) dC[r][c] = (S2[r][c] + S2[c][r]) / T(P - 1);
+            if (ENC == ENC_FULL) {
+#pragma unroll
+                for (int r = 0; r < D; ++r)
+#pragma unroll
+                    for (int c = 0; c < D; ++c) col[D + r * D + c] = dC[r][c];
+            } else {
+                T dUn[D][D];
+                chol_upper_diff<D, T>(Un, dC, dUn);
+#pragma unroll
+                for (int r = 0; r < D; ++r)
+#pragma unroll
+                    for (int c = r; c < D; ++c) col[D + tri<D>(r, c)] = dUn[r][c];
+            }
+        }
+        if (j < NZ) {
+#pragma unroll
+            for (int r = 0; r < NZ; ++r) a.F_z[a.lFz.at(b, t, r * NZ + j)] = col[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < NZ; ++r) a.F_u[a.lFu.at(b, t, r)] = col[r];
+        }
+    }
+}
+
+// clamp the nominal controls of step t into ucur[b] (and park them for the cost pass)
+template <class T>
+__global__ void bnn_lin_control_kernel(int B, int t, const T* U, Layout lU, const T* u_min, const T* u_max,
+                                       T* ucur, T* U_clamped) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    T u = U[lU.at(b, t, 0)];
+    if (u_min && u_max) u = clampv(u, u_min[0], u_max[0]);
+    ucur[b] = u;
+    U_clamped[lU.at(b, t, 0)] = u;
+}
+
+// ------------------------------------------------------------------------------------------
+// rollout: one warp per (problem, alpha)
+// ------------------------------------------------------------------------------------------
+template <class T>
+struct RollStepArgs {
+    int B, N, A, t, P;            // t = -1: initialise (z_0, u_0, J = l(z_0,u_0)); else transition t -> t+1
+    CostParams<T> cost;
+    const T* Xn;                  // [B*A, P, D] particles after the MLP of step t
+    const T* Z; const T* U; const T* k; const T* K; const T* alphas; const T* u_min; const T* u_max;
+    const int32_t* active; const int32_t* bw_status;
+    T* Zall; T* Uall; T* ucur; T* J;          // [B*A, N+1, nz], [B*A, N], [B*A], [B*A]
+    int32_t* status;
+    Layout lZ, lU, lk, lK;
+};
+
+template <class T, int GEO, int ENC>
+__global__ void __launch_bounds__(128) bnn_roll_step_kernel(const RollStepArgs<T> a) {
+    typedef Geo<GEO> G;
+    constexpr int D = G::D, NZ = enc_size(D, ENC), NT = D * (D + 1) / 2;
+    const int lane = threadIdx.x & 31;
+    const long long s = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (s >= (long long)a.B * a.A) return;
+    const int b = (int)(s / a.A), al = (int)(s - (long long)b * a.A);
+    if ((a.active && a.active[b] == 0) || (a.bw_status && a.bw_status[b] != 0)) return;
+    const int P = a.P, t1 = a.t + 1;
+    T zn[NZ];
+    bool ok = true;
+    if (a.t < 0) {
+#pragma unroll
+        for (int e = 0; e < NZ; ++e) zn[e] = a.Z[a.lZ.at(b, 0, e)];
+    } else {
+        T msum[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) msum[d] = T(0);
+        for (int p = lane; p < P; p += 32)
+#pragma unroll
+            for (int d = 0; d < D; ++d) msum[d] += a.Xn[((size_t)s * P + p) * D + d];
+        T M[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) M[d] = warp_sum(msum[d]) / T(P);
+        T csum[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) csum[i] = T(0);
+        for (int p = lane; p < P; p += 32) {
+            T xc[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) xc[d] = a.Xn[((size_t)s * P + p) * D + d] - M[d];
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+                for (int c = r; c < D; ++c) csum[tri<D>(r, c)] += xc[r] * xc[c];
+        }
+        T Cov[D][D], Un[D][D];
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int c = r; c < D; ++c) {
+                T v = warp_sum(csum[tri<D>(r, c)]) / T(P - 1);
+                Cov[r][c] = v;
+                Cov[c][r] = v;
+            }
+        ok = encode_moments<D, ENC, T>(M, Cov, zn, Un);
+    }
+    T* zrow = a.Zall + ((size_t)s * (a.N + 1) + t1) * NZ;
+#pragma unroll
+    for (int e = 0; e < NZ; ++e)
+        if ((e & 31) == lane) zrow[e] = zn[e];
+    if (lane != 0) return;
+    if (!ok && a.status) a.status[b] |= 2;
+    T J = a.t < 0 ? T(0) : a.J[s];
+    if (t1 < a.N) {                                       // control law (ref: ilqr.py:701-719)
+        T du = a.alphas[al] * a.k[a.lk.at(b, t1, 0)];
+#pragma unroll
+        for (int e = 0; e < NZ; ++e) du += (zn[e] - a.Z[a.lZ.at(b, t1, e)]) * a.K[a.lK.at(b, t1, e)];
+        T u = a.U[a.lU.at(b, t1, 0)] + du;
+        if (a.u_min && a.u_max) u = clampv(u, a.u_min[0], a.u_max[0]);
+        a.ucur[s] = u;
+        a.Uall[(size_t)s * a.N + t1] = u;
+        T la, lu, luu;
+        cost_action(a.cost, u, la, lu, luu);
+        J += cost_state<GEO, ENC, T, T>(a.cost, zn, false) + la;
+    } else {
+        J += cost_state<GEO, ENC, T, T>(a.cost, zn, true);
+    }
+    a.J[s] = J;
+}
+
+// argmin over alphas (torch semantics) + copy of the winner, one warp per problem
+template <class T>
+__global__ void bnn_roll_select_kernel(int B, int N, int A, int nz, const T* J, const T* Zall, const T* Uall,
+                                       const int32_t* active, const int32_t* bw_status, T* J_all,
+                                       int32_t* amin, T* J_new, T* Z_new, T* U_new, Layout lZ, Layout lU) {
+    const int lane = threadIdx.x & 31;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    if ((active && active[b] == 0) || (bw_status && bw_status[b] != 0)) return;
+    int best = 0;
+    T bj = J[(size_t)b * A];
+    bool bn = bj != bj;
+    for (int i = 1; i < A; ++i) {
+        T v = J[(size_t)b * A + i];
+        bool vn = v != v;
+        if (!bn && (vn || v < bj)) { best = i; bj = v; bn = vn; }
+    }
+    for (int i = lane; i < A; i += 32) J_all[(size_t)b * A + i] = J[(size_t)b * A + i];
+    if (lane == 0) { amin[b] = best; J_new[b] = bj; }
+    const size_t s = (size_t)b * A + best;
+    for (int i = lane; i < (N + 1) * nz; i += 32) Z_new[lZ.at(b, i / nz, i % nz)] = Zall[s * (N + 1) * nz + i];
+    for (int i = lane; i < N; i += 32) U_new[lU.at(b, i, 0)] = Uall[s * N + i];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <class T>
+struct Workspace {
+    T *W0T, *W1T, *W2T, *Xa, *Xb, *Jp, *ucur, *J, *Zall, *Uall;
+    size_t bytes;
+};
+
+template <class T>
+static Workspace<T> carve(void* base, const pddp_shape* s, const pddp_bnn* n, int A) {
+    const int D = s->geo == GEO_PENDULUM ? 2 : s->geo == GEO_CARTPOLE ? 4 : 6;
+    const int DA = s->geo == GEO_PENDULUM ? 3 : s->geo == GEO_CARTPOLE ? 5 : 8;
+    const size_t K0 = DA + 1, S = (size_t)s->B * (A > 1 ? A : 1), P = n->P;
+    Workspace<T> w;
+    size_t off = 0;
+    auto take = [&](size_t elems) { T* p = reinterpret_cast<T*>(reinterpret_cast<char*>(base) + off); off += ((elems * sizeof(T) + 255) / 256) * 256; return p; };
+    w.W0T = take(K0 * n->H0);
+    w.W1T = take((size_t)n->H0 * n->H1);
+    w.W2T = take((size_t)n->H1 * D);
+    w.Xa = take(S * P * D);
+    w.Xb = take(S * P * D);
+    w.Jp = take((size_t)s->B * P * D * (D + 1));
+    w.ucur = take(S);
+    w.J = take(S);
+    w.Zall = take(S * (s->N + 1) * s->nz);
+    w.Uall = take(S * s->N);
+    w.bytes = off;
+    return w;
+}
+
+template <class T>
+static BnnNet<T> make_net(const pddp_bnn* n, const Workspace<T>& w) {
+    BnnNet<T> r;
+    r.P = n->P; r.H0 = n->H0; r.H1 = n->H1;
+    r.W0T = w.W0T; r.b0 = (const T*)n->b0; r.W1T = w.W1T; r.b1 = (const T*)n->b1; r.W2T = w.W2T; r.b2 = (const T*)n->b2;
+    r.mask0 = (const T*)n->mask0; r.mask1 = (const T*)n->mask1; r.eps0 = (const T*)n->eps0;
+    r.X_mean = (const T*)n->X_mean; r.X_std_inv = (const T*)n->X_std_inv;
+    r.dX_mean = (const T*)n->dX_mean; r.dX_std = (const T*)n->dX_std;
+    return r;
+}
+
+template <class T>
+static cudaError_t prep_weights(const pddp_shape* s, const pddp_bnn* n, const Workspace<T>& w, cudaStream_t st) {
+    const int D = s->geo == GEO_PENDULUM ? 2 : s->geo == GEO_CARTPOLE ? 4 : 6;
+    const int DA = s->geo == GEO_PENDULUM ? 3 : s->geo == GEO_CARTPOLE ? 5 : 8;
+    bnn_transpose_kernel<T><<<8, 256, 0, st>>>((const T*)n->W0, n->H0, DA + 1, n->H0, w.W0T);
+    bnn_transpose_kernel<T><<<64, 256, 0, st>>>((const T*)n->W1, n->H1, n->H0, n->H1, w.W1T);
+    bnn_transpose_kernel<T><<<8, 256, 0, st>>>((const T*)n->W2, 2 * D, n->H1, D, w.W2T);
+    return cudaGetLastError();
+}
+
+// MLP dispatch: SIMT kernel (the tcgen05 kernel hooks in here for fp32 / H = 200)
+template <class T, int GEO, bool TAN, int NJ>
+static cudaError_t launch_mlp_simt(const BnnMlpArgs<T>& a, cudaStream_t st) {
+    constexpr int RPT = sizeof(T) == 4 ? 8 : 4;
+    typedef MlpSmem<T, GEO, NJ, RPT, TAN> SM;
+    auto kern = bnn_mlp_simt_kernel<T, GEO, NJ, RPT, TAN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
+    if (e != cudaSuccess) return e;
+    const long long ntiles = (a.total + SM::NPART - 1) / SM::NPART;
+    const int grid = (int)(ntiles < (long long)num_sms() ? ntiles : (long long)num_sms());
+    kern<<<grid, 256, SM::bytes, st>>>(a);
+    return cudaGetLastError();
+}
+template <class T, int GEO, bool TAN>
+static cudaError_t launch_mlp(const BnnMlpArgs<T>& a, cudaStream_t st) {
+    const int H = a.net.H0 > a.net.H1 ? a.net.H0 : a.net.H1;
+    if (H <= 32) return launch_mlp_simt<T, GEO, TAN, 2>(a, st);
+    if (H <= 208) return launch_mlp_simt<T, GEO, TAN, 13>(a, st);
+    if (H <= 256) return launch_mlp_simt<T, GEO, TAN, 16>(a, st);
+    return cudaErrorInvalidValue;
+}
+
+struct BnnCall {
+    const pddp_shape* s; const pddp_bnn* n; const pddp_cost* cost;
+    const void *z0, *U, *u_min, *u_max; const int32_t* active;
+    void *Z, *F_z, *F_u, *L, *L_z, *L_u, *L_zz, *L_uz, *L_uu, *J_opt; int32_t* status;
+    void* ws; cudaStream_t st;
+};
+
+template <class T>
+static void fill_cost_params(const pddp_cost* c, int DA, CostParams<T>& out) {
+    memset(&out, 0, sizeof(out));
+    for (int i = 0; i < DA * DA; ++i) { out.Q[i] = (T)c->Q[i]; out.Qt[i] = (T)c->Q_term[i]; }
+    for (int i = 0; i < DA; ++i) out.xg[i] = (T)c->x_goal[i];
+    out.R[0] = (T)c->R[0];
+    out.ug[0] = (T)c->u_goal[0];
+}
+
+#define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return e__; } while (0)
+
+template <class T>
+__global__ void bnn_set_z0_kernel(int B, int nz, const T* z0, T* Z, Layout lZ, const int32_t* active) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= B * nz) return;
+    const int b = id / nz, e = id - b * nz;
+    if (active && active[b] != 1) return;
+    Z[lZ.at(b, 0, e)] = z0[id];
+}
+
+template <class T, int GEO, int ENC>
+static cudaError_t linearize_bnn_impl(const BnnCall& c) {
+    typedef Geo<GEO> G;
+    constexpr int D = G::D;
+    const pddp_shape* s = c.s;
+    const int B = s->B, N = s->N, nz = s->nz, nu = s->nu, ly = s->layout, P = c.n->P;
+    Workspace<T> w = carve<T>(c.ws, s, c.n, 1);
+    CK(prep_weights<T>(s, c.n, w, c.st));
+    BnnNet<T> net = make_net<T>(c.n, w);
+    const Layout lZ = make_layout(ly, B, N + 1, nz), lU = make_layout(ly, B, N, nu);
+    T* Z = (T*)c.Z;
+    bnn_set_z0_kernel<T><<<(B * nz + 255) / 256, 256, 0, c.st>>>(B, nz, (const T*)c.z0, Z, lZ, c.active);
+    const long long total = (long long)B * P;
+    bnn_init_particles_kernel<T, GEO, ENC><<<(unsigned)((total + 127) / 128), 128, 0, c.st>>>(
+        Z, lZ, 1, B, P, net.eps0, w.Xa, c.status);
+    CK(cudaGetLastError());
+
+    MomentLinArgs<T> m;
+    m.B = B; m.N = N; m.P = P; m.Jp = w.Jp; m.active = c.active; m.Z = Z; m.F_z = (T*)c.F_z; m.F_u = (T*)c.F_u;
+    m.status = c.status; m.lZ = lZ; m.lFz = make_layout(ly, B, N, nz * nz); m.lFu = make_layout(ly, B, N, nz * nu);
+    const int wpb = 4;
+    const size_t msmem = (size_t)wpb * P * (3 * D + D * D) * sizeof(T);
+    auto mk = bnn_moment_lin_kernel<T, GEO, ENC>;
+    CK(cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+
+    BnnMlpArgs<T> a;
+    a.net = net; a.u = w.ucur; a.Jp = w.Jp; a.total = total;
+    T *cur = w.Xa, *nxt = w.Xb;
+    for (int t = 0; t < N; ++t) {
+        bnn_lin_control_kernel<T><<<(B + 127) / 128, 128, 0, c.st>>>(B, t, (const T*)c.U, lU, (const T*)c.u_min,
+                                                                  (const T*)c.u_max, w.ucur, (T*)c.L_u);
+        a.X = cur; a.Xn = nxt;
+        CK((launch_mlp<T, GEO, true>(a, c.st)));
+        m.t = t; m.X = cur; m.Xn = nxt;
+        mk<<<(B + wpb - 1) / wpb, wpb * 32, msmem, c.st>>>(m);
+        T* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    CK(cudaGetLastError());
+    // cost value / gradient / Hessian over the whole nominal trajectory (clamped u parked in L_u)
+    CostDerivArgs<T> cd;
+    cd.B = B; cd.N = N;
+    fill_cost_params<T>(c.cost, G::DA, cd.cost);
+    cd.Z = Z; cd.U = (const T*)c.L_u; cd.active = c.active;
+    cd.L = (T*)c.L; cd.L_z = (T*)c.L_z; cd.L_u = (T*)c.L_u; cd.L_zz = (T*)c.L_zz; cd.L_uz = (T*)c.L_uz;
+    cd.L_uu = (T*)c.L_uu; cd.J_opt = (T*)c.J_opt;
+    cd.lZ = lZ; cd.lU = lU; cd.lL = make_layout(ly, B, N + 1, 1); cd.lLz = make_layout(ly, B, N + 1, nz);
+    cd.lLu = make_layout(ly, B, N, nu); cd.lLzz = make_layout(ly, B, N + 1, nz * nz);
+    cd.lLuz = make_layout(ly, B, N, nu * nz); cd.lLuu = make_layout(ly, B, N, nu * nu);
+    return cost_derivatives<T>(s->geo, s->enc, cd, c.st);
+}
+
+struct BnnRollCall {
+    const pddp_shape* s; const pddp_bnn* n; const pddp_cost* cost;
+    const void *Z, *U, *k, *K, *alphas; int A; const void *u_min, *u_max;
+    const int32_t *active, *bw_status;
+    void* J_all; int32_t* amin; void *J_new, *Z_new, *U_new; int32_t* status;
+    void* ws; cudaStream_t st;
+};
+
+template <class T, int GEO, int ENC>
+static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
+    typedef Geo<GEO> G;
+    const pddp_shape* s = c.s;
+    const int B = s->B, N = s->N, nz = s->nz, nu = s->nu, ly = s->layout, P = c.n->P, A = c.A;
+    Workspace<T> w = carve<T>(c.ws, s, c.n, A);
+    CK(prep_weights<T>(s, c.n, w, c.st));
+    BnnNet<T> net = make_net<T>(c.n, w);
+    const long long S = (long long)B * A, total = S * P;
+    RollStepArgs<T> r;
+    r.B = B; r.N = N; r.A = A; r.P = P;
+    fill_cost_params<T>(c.cost, G::DA, r.cost);
+    r.Z = (const T*)c.Z; r.U = (const T*)c.U; r.k = (const T*)c.k; r.K = (const T*)c.K; r.alphas = (const T*)c.alphas;
+    r.u_min = (const T*)c.u_min; r.u_max = (const T*)c.u_max; r.active = c.active; r.bw_status = c.bw_status;
+    r.Zall = w.Zall; r.Uall = w.Uall; r.ucur = w.ucur; r.J = w.J; r.status = c.status;
+    r.lZ = make_layout(ly, B, N + 1, nz); r.lU = make_layout(ly, B, N, nu);
+    r.lk = make_layout(ly, B, N, nu); r.lK = make_layout(ly, B, N, nu * nz);
+    bnn_init_particles_kernel<T, GEO, ENC><<<(unsigned)((total + 127) / 128), 128, 0, c.st>>>(
+        r.Z, r.lZ, A, S, P, net.eps0, w.Xa, c.status);
+    const unsigned rgrid = (unsigned)((S * 32 + 127) / 128);
+    r.t = -1; r.Xn = w.Xa;
+    bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 128, 0, c.st>>>(r);
+    CK(cudaGetLastError());
+    BnnMlpArgs<T> a;
+    a.net = net; a.u = w.ucur; a.Jp = nullptr; a.total = total;
+    T *cur = w.Xa, *nxt = w.Xb;
+    for (int t = 0; t < N; ++t) {
+        a.X = cur; a.Xn = nxt;
+        CK((launch_mlp<T, GEO, false>(a, c.st)));
+        r.t = t; r.Xn = nxt;
+        bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 128, 0, c.st>>>(r);
+        T* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    bnn_roll_select_kernel<T><<<(unsigned)(((long long)B * 32 + 127) / 128), 128, 0, c.st>>>(
+        B, N, A, nz, w.J, w.Zall, w.Uall, c.active, c.bw_status, (T*)c.J_all, c.amin, (T*)c.J_new, (T*)c.Z_new,
+        (T*)c.U_new, r.lZ, r.lU);
+    return cudaGetLastError();
+}
+
+#define BNN_DISPATCH(IMPL, call)                                                                          \
+    switch (call.s->geo * 8 + call.s->enc) {                                                              \
+        case GEO_PENDULUM * 8 + ENC_FULL: return IMPL<T, GEO_PENDULUM, ENC_FULL>(call);                   \
+        case GEO_PENDULUM * 8 + ENC_UT: return IMPL<T, GEO_PENDULUM, ENC_UT>(call);                       \
+        case GEO_PENDULUM * 8 + ENC_IGNORE: return IMPL<T, GEO_PENDULUM, ENC_IGNORE>(call);               \
+        case GEO_CARTPOLE * 8 + ENC_FULL: return IMPL<T, GEO_CARTPOLE, ENC_FULL>(call);                   \
+        case GEO_CARTPOLE * 8 + ENC_UT: return IMPL<T, GEO_CARTPOLE, ENC_UT>(call);                       \
+        case GEO_CARTPOLE * 8 + ENC_IGNORE: return IMPL<T, GEO_CARTPOLE, ENC_IGNORE>(call);               \
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_FULL: return IMPL<T, GEO_DOUBLE_CARTPOLE, ENC_FULL>(call);     \
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_UT: return IMPL<T, GEO_DOUBLE_CARTPOLE, ENC_UT>(call);         \
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_IGNORE: return IMPL<T, GEO_DOUBLE_CARTPOLE, ENC_IGNORE>(call); \
+        default: return cudaErrorInvalidValue;                                                            \
+    }
+
+template <class T> static cudaError_t linearize_bnn_t(const BnnCall& c) { BNN_DISPATCH(linearize_bnn_impl, c) }
+template <class T> static cudaError_t rollout_bnn_t(const BnnRollCall& c) { BNN_DISPATCH(rollout_bnn_impl, c) }
+
+}  // namespace pddp
+
+using namespace pddp;
+
+int pddp_capi_fail(int code, const char* msg);          // capi.cu
+int pddp_capi_cuda(cudaError_t e, const char* what);    // capi.cu
+int pddp_capi_check_shape(const pddp_shape* s);         // capi.cu
+
+static int check_bnn(const pddp_shape* s, const pddp_bnn* n) {
+    if (int e = pddp_capi_check_shape(s)) return e;
+    if (s->enc == PDDP_ENC_VARIANCE_ONLY || s->enc == PDDP_ENC_STANDARD_DEVIATION_ONLY)
+        return pddp_capi_fail(PDDP_E_UNSUPPORTED, "BNN: VARIANCE_ONLY / STANDARD_DEVIATION_ONLY not built (SURVEY 8f)");
+    if (s->layout != PDDP_PROBLEM_MAJOR) return pddp_capi_fail(PDDP_E_UNSUPPORTED, "BNN path uses PDDP_PROBLEM_MAJOR");
+    if (!n) return pddp_capi_fail(PDDP_E_BADARG, "bnn is NULL");
+    if (n->P < 2 || n->P > 1024) return pddp_capi_fail(PDDP_E_BADARG, "2 <= particles <= 1024");
+    if (n->H0 < 1 || n->H1 < 1 || n->H0 > 256 || n->H1 > 256) return pddp_capi_fail(PDDP_E_UNSUPPORTED, "hidden widths must be in [1,256]");
+    if (!n->W0 || !n->b0 || !n->W1 || !n->b1 || !n->W2 || !n->b2 || !n->mask0 || !n->mask1 || !n->eps0)
+        return pddp_capi_fail(PDDP_E_BADARG, "bnn: NULL weight / mask / eps0 pointer");
+    return 0;
+}
+
+extern "C" int64_t pddp_bnn_workspace_bytes(const pddp_shape* s, const pddp_bnn* n, int32_t A) {
+    if (int e = check_bnn(s, n)) return e;
+    if (A < 1 || A > 64) return pddp_capi_fail(PDDP_E_BADARG, "1 <= A <= 64");
+    if (s->dtype == PDDP_F32) return (int64_t)carve<float>(nullptr, s, n, A).bytes;
+    return (int64_t)carve<double>(nullptr, s, n, A).bytes;
+}
+
+extern "C" int pddp_linearize_bnn(const pddp_shape* s, const pddp_bnn* n, const pddp_cost* cost, const void* z0,
+                                  const void* U, const void* u_min, const void* u_max, const int32_t* active,
+                                  void* Z, void* F_z, void* F_u, void* L, void* L_z, void* L_u, void* L_zz,
+                                  void* L_uz, void* L_uu, void* J_opt, int32_t* status, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+    if (int e = check_bnn(s, n)) return e;
+    if (!cost || !z0 || !U || !Z || !F_z || !F_u || !L || !L_z || !L_u || !L_zz || !L_uz || !L_uu || !J_opt || !workspace)
+        return pddp_capi_fail(PDDP_E_BADARG, "pddp_linearize_bnn: NULL argument");
+    if ((u_min == nullptr) != (u_max == nullptr)) return pddp_capi_fail(PDDP_E_BADARG, "u_min and u_max must be given together");
+    if (workspace_bytes < pddp_bnn_workspace_bytes(s, n, 1)) return pddp_capi_fail(PDDP_E_BADARG, "workspace too small");
+    BnnCall c{s, n, cost, z0, U, u_min, u_max, active, Z, F_z, F_u, L, L_z, L_u, L_zz, L_uz, L_uu, J_opt, status,
+              workspace, (cudaStream_t)stream};
+    cudaError_t e = s->dtype == PDDP_F32 ? linearize_bnn_t<float>(c) : linearize_bnn_t<double>(c);
+    return pddp_capi_cuda(e, "pddp_linearize_bnn");
+}
+
+extern "C" int pddp_rollout_bnn(const pddp_shape* s, const pddp_bnn* n, const pddp_cost* cost, const void* Z,
+                                const void* U, const void* k, const void* K, const void* alphas, int32_t A,
+                                const void* u_min, const void* u_max, const int32_t* active,
+                                const int32_t* bw_status, void* J_all, int32_t* amin, void* J_new, void* Z_new,
+                                void* U_new, int32_t* status, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
+    if (int e = check_bnn(s, n)) return e;
+    if (!cost || !Z || !U || !k || !K || !alphas || !J_all || !amin || !J_new || !Z_new || !U_new || !workspace)
+        return pddp_capi_fail(PDDP_E_BADARG, "pddp_rollout_bnn: NULL argument");
+    if (A < 1 || A > 64) return pddp_capi_fail(PDDP_E_BADARG, "1 <= A <= 64");
+    if ((u_min == nullptr) != (u_max == nullptr)) return pddp_capi_fail(PDDP_E_BADARG, "u_min and u_max must be given together");
+    if (workspace_bytes < pddp_bnn_workspace_bytes(s, n, A)) return pddp_capi_fail(PDDP_E_BADARG, "workspace too small");
+    BnnRollCall c{s, n, cost, Z, U, k, K, alphas, A, u_min, u_max, active, bw_status, J_all, amin, J_new, Z_new, U_new,
+                  status, workspace, (cudaStream_t)stream};
+    cudaError_t e = s->dtype == PDDP_F32 ? rollout_bnn_t<float>(c) : rollout_bnn_t<double>(c);
+    return pddp_capi_cuda(e, "pddp_rollout_bnn");
+}

@@ -1,0 +1,150 @@
+// Shared pieces of the BNN path: network descriptor, small dense linear algebra on register arrays
+// (Cholesky with the reference's escalating jitter, its differential, triangular solves).
+#pragma once
+#include "core.cuh"
+
+namespace pddp {
+
+template <class T>
+struct BnnNet {
+    int P, H0, H1;
+    const T *W0T, *b0, *W1T, *b1, *W2T, *b2;   // transposed copies: W0T[K0][H0], W1T[H0][H1], W2T[H1][D]
+    const T *mask0, *mask1, *eps0;             // [P,H0], [P,H1], [P,D]
+    const T *X_mean, *X_std_inv, *dX_mean, *dX_std;   // nullptr = 0 / 1 defaults (ref: modules.py:93-98)
+};
+
+// Upper Cholesky factor, U^T U = C + jitter*I, reading the upper triangle of C.
+template <int D, class T>
+__device__ __forceinline__ bool chol_upper(const T (&C)[D][D], T jitter, T (&U)[D][D]) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            if (j < i) { U[i][j] = T(0); continue; }
+            T s = C[i][j] + (i == j ? jitter : T(0));
+#pragma unroll
+            for (int k = 0; k < i; ++k) s -= U[k][i] * U[k][j];
+            if (i == j) {
+                if (!(s > T(0))) ok = false;
+                U[i][i] = jsqrt(s);
+            } else {
+                U[i][j] = s / U[i][i];
+            }
+        }
+    }
+    return ok;
+}
+
+// ref: pddp/utils/encoding.py:536-564 -- jitter 1e-12 is always added, x10 until it exceeds 10.
+template <int D, class T>
+__device__ __forceinline__ bool chol_upper_jitter(const T (&C)[D][D], T (&U)[D][D]) {
+    double jitter = 1e-12;
+    while (true) {
+        if (chol_upper<D, T>(C, (T)jitter, U)) return true;
+        jitter *= 10.0;
+        if (jitter > 10.0) return false;
+    }
+}
+
+// Differential of the upper Cholesky factor: given U (C = U^T U) and a SYMMETRIC dC, returns
+// dU = Phi(U^-T dC U^-1) U with Phi = upper triangle, halved diagonal.  This is the forward-mode
+// counterpart of torch's (symmetrised) Cholesky backward.
+template <int D, class T>
+__device__ __forceinline__ void chol_upper_diff(const T (&U)[D][D], const T (&dC)[D][D], T (&dU)[D][D]) {
+    T Y[D][D];   // Y = U^-T dC  (forward substitution, U^T is lower)
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            T s = dC[i][c];
+#pragma unroll
+            for (int k = 0; k < i; ++k) s -= U[k][i] * Y[k][c];
+            Y[i][c] = s / U[i][i];
+        }
+    T A[D][D];   // A = Y U^-1  (row-wise: a U = y)
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            T s = Y[r][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s -= A[r][k] * U[k][j];
+            A[r][j] = s / U[j][j];
+        }
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            if (c < r) { dU[r][c] = T(0); continue; }
+            T s = T(0);
+#pragma unroll
+            for (int k = r; k <= c; ++k) s += (k == r ? T(0.5) * A[r][k] : A[r][k]) * U[k][c];
+            dU[r][c] = s;
+        }
+}
+
+// eps = delta U^-1   (row vector times inverse of upper-triangular U)   ref: modules.py:335-348
+template <int D, class T>
+__device__ __forceinline__ void solve_right_upper(const T (&U)[D][D], const T* delta, T* eps) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        T s = delta[c];
+#pragma unroll
+        for (int r = 0; r < c; ++r) s -= eps[r] * U[r][c];
+        eps[c] = s / U[c][c];
+    }
+}
+
+// U = decode_covar_sqrt(z)   ref: pddp/utils/encoding.py:304-362
+template <int D, int ENC, class T>
+__device__ __forceinline__ bool load_factor(const T* z, T (&U)[D][D]) {
+    if (ENC == ENC_FULL) {
+        T C[D][D];
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = 0; b < D; ++b) C[a][b] = T(0.5) * (z[D + a * D + b] + z[D + b * D + a]);
+        return chol_upper_jitter<D, T>(C, U);
+    }
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int b = 0; b < D; ++b) {
+            if (ENC == ENC_UT) U[a][b] = b >= a ? z[D + tri<D>(a, b)] : T(0);
+            else U[a][b] = a == b ? T(1e-3) : T(0);
+        }
+    return true;
+}
+
+// z' = encode(M, C=Cov)  for FULL / UT / IGNORE    ref: pddp/utils/encoding.py:99-141
+template <int D, int ENC, class T>
+__device__ __forceinline__ bool encode_moments(const T* M, const T (&Cov)[D][D], T* zn, T (&Un)[D][D]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) zn[i] = M[i];
+    if (ENC == ENC_FULL) {
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = 0; b < D; ++b) zn[D + a * D + b] = Cov[a][b];
+        return true;
+    }
+    if (ENC == ENC_UT) {
+        bool ok = chol_upper_jitter<D, T>(Cov, Un);
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = a; b < D; ++b) zn[D + tri<D>(a, b)] = Un[a][b];
+        return ok;
+    }
+    return true;
+}
+
+template <class T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+}  // namespace pddp

@@ -43,6 +43,10 @@ static void fill_cost(const pddp_cost* c, int DA, CostParams<T>& out) {
     out.ug[0] = (T)c->u_goal[0];
 }
 
+int pddp_capi_fail(int code, const char* msg) { return fail(code, msg); }
+int pddp_capi_cuda(cudaError_t e, const char* what) { return cuda_result(e, what); }
+int pddp_capi_check_shape(const pddp_shape* s) { return check_shape(s); }
+
 extern "C" const char* pddp_version(void) { return "pddp_b200 0.1 (sm_100a)"; }
 extern "C" const char* pddp_last_error(void) { return g_err; }
 

@@ -43,6 +43,45 @@ class KnownDynamics:
         return s
 
 
+class BNNDynamics:
+    """Eval-mode MC-dropout BNN: weights, persistent dropout masks [P,H] and eps_in[0] [P,D]
+    (ref: pddp/models/bnn/modules.py:287-386).  Two hidden layers."""
+
+    def __init__(self, geo, weights, biases, masks, eps0, X_mean=None, X_std_inv=None,
+                 dX_mean=None, dX_std=None):
+        if len(weights) != 3 or len(biases) != 3 or len(masks) != 2:
+            raise NotImplementedError("pddp_b200: the BNN path supports exactly two hidden layers")
+        self.geo = geo
+        self.is_bnn = True
+        self.tensors = dict(W0=weights[0], W1=weights[1], W2=weights[2], b0=biases[0], b1=biases[1],
+                            b2=biases[2], mask0=masks[0], mask1=masks[1], eps0=eps0, X_mean=X_mean,
+                            X_std_inv=X_std_inv, dX_mean=dX_mean, dX_std=dX_std)
+        self.P = int(eps0.shape[0])
+        self.H0, self.H1 = int(weights[0].shape[0]), int(weights[1].shape[0])
+        D, nu, ang, _ = _lib.GEO_INFO[geo]
+        DA = D + len(ang)
+        if tuple(weights[0].shape) != (self.H0, DA + nu) or tuple(weights[1].shape) != (self.H1, self.H0) \
+                or tuple(weights[2].shape) != (2 * D, self.H1):
+            raise ValueError("BNN weight shapes do not match the geometry")
+        if tuple(masks[0].shape) != (self.P, self.H0) or tuple(masks[1].shape) != (self.P, self.H1) \
+                or tuple(eps0.shape) != (self.P, D):
+            raise ValueError("BNN mask / eps0 shapes must be [P,H] / [P,D]")
+        self._device_copies = {}
+
+    def c_struct(self, dtype, device):
+        key = (dtype, str(device))
+        if key not in self._device_copies:
+            self._device_copies[key] = {
+                k: None if v is None else torch.as_tensor(v).detach().to(dtype=dtype, device=device).contiguous()
+                for k, v in self.tensors.items()}
+        t = self._device_copies[key]
+        s = _lib.BNN()
+        s.P, s.H0, s.H1 = self.P, self.H0, self.H1
+        for k, v in t.items():
+            setattr(s, k, None if v is None else v.data_ptr())
+        return s
+
+
 class QRCostConstants:
     """Q, R, Q_term, x_goal, u_goal of a QRCost on the augmented state (ref: costs/quadratic.py)."""
 

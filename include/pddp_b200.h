@@ -198,6 +198,15 @@ int pddp_cost_derivatives(const pddp_shape* shape, const pddp_cost* cost, const 
                           const void* U, const int32_t* active, void* L, void* L_z, void* L_u,
                           void* L_zz, void* L_uz, void* L_uu, void* J_opt, void* stream);
 
+/* ---- instrumentation (bench.py) -----------------------------------------------------------------
+ * pddp_profile_enable(1) makes the BNN path bracket its kernels with CUDA events on the launch
+ * stream; pddp_profile_read synchronises and returns total milliseconds / launch counts for
+ * kind 0 = MLP (linearise), 1 = MLP (rollout), 2 = moment matching (linearise), 3 = rollout step.
+ * pddp_launch_count() = kernels launched by this library since load.                          */
+void pddp_profile_enable(int on);
+int pddp_profile_read(double* ms, int64_t* count);
+int64_t pddp_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@
 #include "bnn_common.cuh"
 #include "bnn_mlp_simt.cuh"
 #include "kernels.h"
+#include "profile.h"
 #include <stdio.h>
 
 namespace pddp {
@@ -504,9 +505,13 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
         bnn_lin_control_kernel<T><<<(B + 127) / 128, 128, 0, c.st>>>(B, t, (const T*)c.U, lU, (const T*)c.u_min,
                                                                   (const T*)c.u_max, w.ucur, (T*)c.L_u);
         a.X = cur; a.Xn = nxt;
+        prof_begin(PROF_MLP_LIN, c.st);
         CK((launch_mlp<T, GEO, true>(a, c.st)));
+        prof_end(PROF_MLP_LIN, c.st);
         m.t = t; m.X = cur; m.Xn = nxt;
+        prof_begin(PROF_MOMENT_LIN, c.st);
         mk<<<(B + wpb - 1) / wpb, wpb * 32, msmem, c.st>>>(m);
+        prof_end(PROF_MOMENT_LIN, c.st);
         T* tmp = cur; cur = nxt; nxt = tmp;
     }
     CK(cudaGetLastError());
@@ -520,6 +525,7 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
     cd.lZ = lZ; cd.lU = lU; cd.lL = make_layout(ly, B, N + 1, 1); cd.lLz = make_layout(ly, B, N + 1, nz);
     cd.lLu = make_layout(ly, B, N, nu); cd.lLzz = make_layout(ly, B, N + 1, nz * nz);
     cd.lLuz = make_layout(ly, B, N, nu * nz); cd.lLuu = make_layout(ly, B, N, nu * nu);
+    note_launches(3 + 2 + 3LL * N + 2);
     return cost_derivatives<T>(s->geo, s->enc, cd, c.st);
 }
 
@@ -559,14 +565,19 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     T *cur = w.Xa, *nxt = w.Xb;
     for (int t = 0; t < N; ++t) {
         a.X = cur; a.Xn = nxt;
+        prof_begin(PROF_MLP_ROLL, c.st);
         CK((launch_mlp<T, GEO, false>(a, c.st)));
+        prof_end(PROF_MLP_ROLL, c.st);
         r.t = t; r.Xn = nxt;
+        prof_begin(PROF_ROLL_STEP, c.st);
         bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 128, 0, c.st>>>(r);
+        prof_end(PROF_ROLL_STEP, c.st);
         T* tmp = cur; cur = nxt; nxt = tmp;
     }
     bnn_roll_select_kernel<T><<<(unsigned)(((long long)B * 32 + 127) / 128), 128, 0, c.st>>>(
         B, N, A, nz, w.J, w.Zall, w.Uall, c.active, c.bw_status, (T*)c.J_all, c.amin, (T*)c.J_new, (T*)c.Z_new,
         (T*)c.U_new, r.lZ, r.lU);
+    note_launches(3 + 2 + 2LL * N + 1);
     return cudaGetLastError();
 }
 

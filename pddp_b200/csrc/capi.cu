@@ -2,6 +2,7 @@
 // conversion of the by-value parameter structs, dtype dispatch.  No allocation, no synchronisation.
 #include "../../include/pddp_b200.h"
 #include "kernels.h"
+#include "profile.h"
 #include <stdio.h>
 #include <string.h>
 
@@ -76,6 +77,7 @@ static int linearize_known_t(const pddp_shape* s, const pddp_known_dynamics* dyn
     // (the only thread that reads U[b,t] is the one that overwrites L_u[b,t]).
     a.U_clamped = s->enc == PDDP_ENC_IGNORE_UNCERTAINTY ? nullptr : (T*)L_u;
     if (int e = cuda_result(linearize_known<T>(s->geo, s->enc, a, st), "pddp_linearize_known")) return e;
+    note_launches(s->enc == PDDP_ENC_IGNORE_UNCERTAINTY ? 1 : 3);
     if (s->enc == PDDP_ENC_IGNORE_UNCERTAINTY) return 0;
     CostDerivArgs<T> c;
     c.B = s->B; c.N = s->N; c.cost = a.cost; c.Z = a.Z; c.U = (const T*)L_u; c.active = active;
@@ -119,6 +121,7 @@ static int backward_t(const pddp_shape* s, const void* F_z, const void* F_u, con
     a.lLzz = make_layout(ly, B, N + 1, nz * nz); a.lLuz = make_layout(ly, B, N, nu * nz);
     a.lLuu = make_layout(ly, B, N, nu * nu); a.lU = make_layout(ly, B, N, nu);
     a.lk = make_layout(ly, B, N, nu); a.lK = make_layout(ly, B, N, nu * nz);
+    note_launches(1);
     return cuda_result(backward_pass<T>(a, s->layout, st), "pddp_backward");
 }
 
@@ -154,6 +157,7 @@ static int rollout_known_t(const pddp_shape* s, const pddp_known_dynamics* dyn, 
     const int64_t B = s->B, N = s->N, nz = s->nz, nu = s->nu, ly = s->layout;
     a.lZ = make_layout(ly, B, N + 1, nz); a.lU = make_layout(ly, B, N, nu);
     a.lk = make_layout(ly, B, N, nu); a.lK = make_layout(ly, B, N, nu * nz);
+    note_launches(1);
     return cuda_result(rollout_known<T>(s->geo, s->enc, a, st), "pddp_rollout_known");
 }
 
@@ -188,6 +192,7 @@ static int accept_t(const pddp_shape* s, const void* J_new, const int32_t* bw_st
     a.iters_left = iters_left; a.active = active; a.Z = (T*)Z; a.U = (T*)U; a.n_active = n_active;
     a.lZ = make_layout(s->layout, s->B, s->N + 1, s->nz);
     a.lU = make_layout(s->layout, s->B, s->N, s->nu);
+    note_launches(2);
     return cuda_result(accept_update<T>(a, accepted, st), "pddp_accept_update");
 }
 
@@ -221,6 +226,7 @@ static int cost_derivs_t(const pddp_shape* s, const pddp_cost* cost, const void*
     a.lL = make_layout(ly, B, N + 1, 1); a.lLz = make_layout(ly, B, N + 1, nz);
     a.lLu = make_layout(ly, B, N, nu); a.lLzz = make_layout(ly, B, N + 1, nz * nz);
     a.lLuz = make_layout(ly, B, N, nu * nz); a.lLuu = make_layout(ly, B, N, nu * nu);
+    note_launches(a.J_opt ? 2 : 1);
     return cuda_result(cost_derivatives<T>(s->geo, s->enc, a, st), "pddp_cost_derivatives");
 }
 

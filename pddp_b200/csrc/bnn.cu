@@ -14,9 +14,11 @@
 #include "../../include/pddp_b200.h"
 #include "bnn_common.cuh"
 #include "bnn_mlp_simt.cuh"
+#include "bnn_mlp_tc.cuh"
 #include "kernels.h"
 #include "profile.h"
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace pddp {
 
@@ -377,7 +379,8 @@ static int num_sms() {
 
 template <class T>
 struct Workspace {
-    T *W0T, *W1T, *W2T, *Xa, *Xb, *Jp, *ucur, *J, *Zall, *Uall;
+    T *W0T, *W1T, *W2T, *m0T, *m1T, *Xa, *Xb, *Jp, *ucur, *J, *Zall, *Uall;
+    float* Bimg;   // tcgen05 path: pre-swizzled hi/lo TF32 images of W1, [kb][hi|lo][208 x 128 B]
     size_t bytes;
 };
 
@@ -392,6 +395,8 @@ static Workspace<T> carve(void* base, const pddp_shape* s, const pddp_bnn* n, in
     w.W0T = take(K0 * n->H0);
     w.W1T = take((size_t)n->H0 * n->H1);
     w.W2T = take((size_t)n->H1 * D);
+    w.m0T = take((size_t)n->H0 * P);
+    w.m1T = take((size_t)n->H1 * P);
     w.Xa = take(S * P * D);
     w.Xb = take(S * P * D);
     w.Jp = take((size_t)s->B * P * D * (D + 1));
@@ -399,6 +404,7 @@ static Workspace<T> carve(void* base, const pddp_shape* s, const pddp_bnn* n, in
     w.J = take(S);
     w.Zall = take(S * (s->N + 1) * s->nz);
     w.Uall = take(S * s->N);
+    w.Bimg = reinterpret_cast<float*>(take((size_t)tc::MAX_KB * tc::B_STAGE_BYTES / sizeof(T)));
     w.bytes = off;
     return w;
 }
@@ -409,9 +415,19 @@ static BnnNet<T> make_net(const pddp_bnn* n, const Workspace<T>& w) {
     r.P = n->P; r.H0 = n->H0; r.H1 = n->H1;
     r.W0T = w.W0T; r.b0 = (const T*)n->b0; r.W1T = w.W1T; r.b1 = (const T*)n->b1; r.W2T = w.W2T; r.b2 = (const T*)n->b2;
     r.mask0 = (const T*)n->mask0; r.mask1 = (const T*)n->mask1; r.eps0 = (const T*)n->eps0;
+    r.mask0T = w.m0T; r.mask1T = w.m1T;
     r.X_mean = (const T*)n->X_mean; r.X_std_inv = (const T*)n->X_std_inv;
     r.dX_mean = (const T*)n->dX_mean; r.dX_std = (const T*)n->dX_std;
     return r;
+}
+
+// The tcgen05 kernel covers fp32 with hidden widths in (64, 208] x (64, 224]; everything else
+// (fp64, small nets) runs the SIMT kernel.  PDDP_FORCE_SIMT=1 disables it (A/B comparisons).
+template <class T> static bool use_tensor_cores(int H0, int H1) { return false; }
+template <> bool use_tensor_cores<float>(int H0, int H1) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("PDDP_FORCE_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
+    return !forced && H0 > 64 && H0 <= tc::MAX_KB * tc::KBLK && H1 > 64 && H1 <= tc::TILE_N && H0 % 4 == 0 && H1 % 4 == 0;
 }
 
 template <class T>
@@ -421,6 +437,10 @@ static cudaError_t prep_weights(const pddp_shape* s, const pddp_bnn* n, const Wo
     bnn_transpose_kernel<T><<<8, 256, 0, st>>>((const T*)n->W0, n->H0, DA + 1, n->H0, w.W0T);
     bnn_transpose_kernel<T><<<64, 256, 0, st>>>((const T*)n->W1, n->H1, n->H0, n->H1, w.W1T);
     bnn_transpose_kernel<T><<<8, 256, 0, st>>>((const T*)n->W2, 2 * D, n->H1, D, w.W2T);
+    bnn_transpose_kernel<T><<<16, 256, 0, st>>>((const T*)n->mask0, n->P, n->H0, n->P, w.m0T);
+    bnn_transpose_kernel<T><<<16, 256, 0, st>>>((const T*)n->mask1, n->P, n->H1, n->P, w.m1T);
+    if (use_tensor_cores<T>(n->H0, n->H1))
+        tc::bnn_tc_prep_kernel<<<64, 256, 0, st>>>((const float*)n->W1, n->H0, n->H1, (n->H0 + tc::KBLK - 1) / tc::KBLK, w.Bimg);
     return cudaGetLastError();
 }
 
@@ -437,8 +457,23 @@ static cudaError_t launch_mlp_simt(const BnnMlpArgs<T>& a, cudaStream_t st) {
     kern<<<grid, 256, SM::bytes, st>>>(a);
     return cudaGetLastError();
 }
+template <int GEO, bool TAN>
+static cudaError_t launch_mlp_tc(const BnnMlpArgs<float>& a, const float* Bimg, cudaStream_t st) {
+    constexpr int RPP = TAN ? Geo<GEO>::D + 2 : 1, NPART = 4 * (32 / RPP);
+    auto kern = tc::bnn_mlp_tc_kernel<GEO, TAN>;
+    const int smem = tc::Smem::TOTAL + 1024;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const long long ntiles = (a.total + NPART - 1) / NPART;
+    const int grid = (int)(ntiles < (long long)num_sms() ? ntiles : (long long)num_sms());
+    kern<<<grid, tc::THREADS, smem, st>>>(a, Bimg, (a.net.H0 + tc::KBLK - 1) / tc::KBLK);
+    return cudaGetLastError();
+}
 template <class T, int GEO, bool TAN>
-static cudaError_t launch_mlp(const BnnMlpArgs<T>& a, cudaStream_t st) {
+static cudaError_t launch_mlp(const BnnMlpArgs<T>& a, const float* Bimg, cudaStream_t st) {
+    if (use_tensor_cores<T>(a.net.H0, a.net.H1)) {
+        if constexpr (sizeof(T) == 4) return launch_mlp_tc<GEO, TAN>(a, Bimg, st);
+    }
     const int H = a.net.H0 > a.net.H1 ? a.net.H0 : a.net.H1;
     if (H <= 32) return launch_mlp_simt<T, GEO, TAN, 2>(a, st);
     if (H <= 208) return launch_mlp_simt<T, GEO, TAN, 13>(a, st);
@@ -506,7 +541,7 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
                                                                   (const T*)c.u_max, w.ucur, (T*)c.L_u);
         a.X = cur; a.Xn = nxt;
         prof_begin(PROF_MLP_LIN, c.st);
-        CK((launch_mlp<T, GEO, true>(a, c.st)));
+        CK((launch_mlp<T, GEO, true>(a, w.Bimg, c.st)));
         prof_end(PROF_MLP_LIN, c.st);
         m.t = t; m.X = cur; m.Xn = nxt;
         prof_begin(PROF_MOMENT_LIN, c.st);
@@ -525,7 +560,7 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
     cd.lZ = lZ; cd.lU = lU; cd.lL = make_layout(ly, B, N + 1, 1); cd.lLz = make_layout(ly, B, N + 1, nz);
     cd.lLu = make_layout(ly, B, N, nu); cd.lLzz = make_layout(ly, B, N + 1, nz * nz);
     cd.lLuz = make_layout(ly, B, N, nu * nz); cd.lLuu = make_layout(ly, B, N, nu * nu);
-    note_launches(3 + 2 + 3LL * N + 2);
+    note_launches(6 + 2 + 3LL * N + 2);
     return cost_derivatives<T>(s->geo, s->enc, cd, c.st);
 }
 
@@ -566,7 +601,7 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     for (int t = 0; t < N; ++t) {
         a.X = cur; a.Xn = nxt;
         prof_begin(PROF_MLP_ROLL, c.st);
-        CK((launch_mlp<T, GEO, false>(a, c.st)));
+        CK((launch_mlp<T, GEO, false>(a, w.Bimg, c.st)));
         prof_end(PROF_MLP_ROLL, c.st);
         r.t = t; r.Xn = nxt;
         prof_begin(PROF_ROLL_STEP, c.st);
@@ -577,7 +612,7 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     bnn_roll_select_kernel<T><<<(unsigned)(((long long)B * 32 + 127) / 128), 128, 0, c.st>>>(
         B, N, A, nz, w.J, w.Zall, w.Uall, c.active, c.bw_status, (T*)c.J_all, c.amin, (T*)c.J_new, (T*)c.Z_new,
         (T*)c.U_new, r.lZ, r.lU);
-    note_launches(3 + 2 + 2LL * N + 1);
+    note_launches(6 + 2 + 2LL * N + 1);
     return cudaGetLastError();
 }
 

@@ -10,6 +10,7 @@ struct BnnNet {
     int P, H0, H1;
     const T *W0T, *b0, *W1T, *b1, *W2T, *b2;   // transposed copies: W0T[K0][H0], W1T[H0][H1], W2T[H1][D]
     const T *mask0, *mask1, *eps0;             // [P,H0], [P,H1], [P,D]
+    const T *mask0T, *mask1T;                  // transposed copies [H0,P], [H1,P] (coalesced when lanes = particles)
     const T *X_mean, *X_std_inv, *dX_mean, *dX_std;   // nullptr = 0 / 1 defaults (ref: modules.py:93-98)
 };
 

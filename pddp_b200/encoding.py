@@ -99,3 +99,17 @@ def decode_covar(Z, encoding=StateEncoding.DEFAULT, state_size=None):
 def decode_var(Z, encoding=StateEncoding.DEFAULT, state_size=None):
     """ref: pddp/utils/encoding.py:219-258"""
     return torch.diagonal(decode_covar(Z, encoding, state_size), dim1=-2, dim2=-1)
+
+
+class GaussianVariable:
+    """Minimal stand-in for pddp.utils.gaussian_variable.GaussianVariable: what `env.get_state()`
+    returns and the controller encodes (ref: pddp/envs/gym_env.py:75-85, controllers/ilqr.py:285)."""
+
+    def __init__(self, mean, covar=None, var=None, std=None):
+        self._mean, self._covar, self._var, self._std = mean, covar, var, std
+
+    def mean(self):
+        return self._mean
+
+    def encode(self, encoding=StateEncoding.DEFAULT):
+        return encode(self._mean, C=self._covar, V=self._var, S=self._std, encoding=encoding)

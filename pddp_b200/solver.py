@@ -240,6 +240,14 @@ class BatchedSolver:
                 p(self.lin_status), _lib.stream_ptr())
             _lib.check(code, "linearize_known")
 
+    def cost_only(self):
+        """Cost value / gradient / Hessian of whatever is stored in Z, U (no rollout)."""
+        b, p = self.buf, _lib.ptr
+        code = self.lib.pddp_cost_derivatives(
+            C.byref(self.shape), C.byref(self.c_cost), p(b["Z"]), p(b["U"]), None, p(b["L"]), p(b["L_z"]),
+            p(b["L_u"]), p(b["L_zz"]), p(b["L_uz"]), p(b["L_uu"]), p(self.J_opt), _lib.stream_ptr())
+        _lib.check(code, "cost_derivatives")
+
     def backward(self, use_active=True):
         b, p = self.buf, _lib.ptr
         code = self.lib.pddp_backward(

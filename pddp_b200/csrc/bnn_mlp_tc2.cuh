@@ -1,0 +1,563 @@
+// Particle MLP on the 5th-generation tensor cores, second design: BOTH dense layers on tcgen05,
+// particle-uniform tiles, and one streamed W1 K-block shared by two row tiles.
+//
+//   X'_p = X_p + dX_std * fc_out(relu(M1_p * fc_1(relu(M0_p * fc_0(norm([aug(X_p), u])))))) + dX_mean
+//   (ref: pddp/models/bnn/modules.py:200-264, 774-789; dropout masks are [P,H], one row per particle)
+//
+// What changed against bnn_mlp_tc.cuh and why (ncu, profiles/r1_summary.md): that kernel spent its
+// time on CUDA-core work around the MMAs (layer 0 as FFMAs with broadcast LDS of W0, per-row mask
+// loads from L2, 27 SASS instructions per hidden unit) and moved 7 GB per launch from L2 (the W1
+// images once per 128-row tile, the mask rows once per row).  Here
+//   * a tile holds 128 rows of ONE particle p (rows gathered with stride P), so the dropout masks
+//     are per-column constants of the tile: M0_p is folded into a per-particle image of W0|b0
+//     (relu(m*x) = m*relu(x), m >= 0) and M1_p into a per-particle copy of the output weights --
+//     no mask is read in the inner loops at all;
+//   * layer 0 runs on the tensor core too: A0 = [norm(aug(X),u), 1] (K padded to 8/16) times the
+//     per-particle image, 3xTF32, 32 hidden units at a time into a small TMEM accumulator.  Row
+//     H0 of the image is the unit vector of the bias column, so hidden unit H0 is the constant 1
+//     that carries b1 through the second GEMM (b1 is column H0 of the W1 image);
+//   * two independent tile "tracks" per CTA consume the same streamed W1 K-block (16 wide,
+//     SWIZZLE_64B, hi|lo TF32 parts): half the L2->smem traffic per row.  Track 1 runs half a
+//     tile behind track 0, so one track's epilogue/input phase is covered by the other's MMAs;
+//   * warp roles (18 warps): 4 epilogue + 4 mid-stage warps per track, 1 bulk-copy loader, 1 MMA
+//     issuer.  mid-stage = tcgen05.ld of the layer-0 accumulator, ReLU (tangent rows gated by
+//     their primal row via __ballot_sync), hi/lo split, st.shared into the UMMA K-major layout.
+//
+// TMEM (512 columns): track t owns columns [256t, 256t+208) for the layer-1 accumulator and
+// [256t+208, 256t+240) for the layer-0 chunk.
+#pragma once
+#include "bnn_mlp_tc.cuh"
+
+namespace pddp {
+namespace tc2 {
+
+using tc::bulk_g2s;
+using tc::fence_async_smem;
+using tc::mbar_arrive;
+using tc::mbar_expect_tx;
+using tc::mbar_init;
+using tc::mbar_wait;
+using tc::smem_u32;
+using tc::tc_commit;
+using tc::tc_fence_after;
+using tc::tc_fence_before;
+using tc::tc_mma_tf32;
+
+constexpr int TILE_M = 128, TILE_N = 208, KB = 16, MAX_NKB = 13, MAX_NCH = 7, N0 = 32;
+constexpr int B_PART = TILE_N * 64;    // one hi or lo part of a W1 K-block: 208 rows x 16 tf32
+constexpr int B_STAGE = 2 * B_PART;    // 26 624 B
+constexpr int A1_PART = TILE_M * 64;   // 128 rows x 16 tf32
+constexpr int A1_SLOT = 2 * A1_PART;   // 16 384 B
+constexpr int THREADS = 18 * 32;
+constexpr int TM_ACC1 = 0, TM_ACC0 = 208, TM_TRACK = 256;
+
+// byte offset of element (row, kk) in a K-major tile whose rows are ROWB bytes (32 / 64 / 128 =
+// SWIZZLE_32B / 64B / 128B): 16-byte chunk index XORed with the matching bits of the row index.
+template <int ROWB>
+__host__ __device__ __forceinline__ uint32_t swz(int row, int kk) {
+    constexpr int SH = ROWB == 32 ? 2 : ROWB == 64 ? 1 : 0;
+    const int chunk = (kk >> 2) ^ ((row & 7) >> SH);
+    return (uint32_t)((row >> 3) * (8 * ROWB) + (row & 7) * ROWB + (chunk << 4) + (kk & 3) * 4);
+}
+// K-major shared-memory descriptor for rows of ROWB bytes (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) addr>>4, [16,30) LBO>>4 = 1, [32,46) SBO>>4 = 8 rows, [46,48) version 1, [61,64) layout type.
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    constexpr uint64_t LT = ROWB == 32 ? 6 : ROWB == 64 ? 4 : 2;
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= LT << 61;
+    return d;
+}
+constexpr uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// hi = x rounded to TF32 (round half away, like cvt.rna), lo = (x - hi) truncated to TF32
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
+}
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled
+// above the wait.
+__device__ __forceinline__ void tc_wait_ld16(float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+__device__ __forceinline__ void tc_wait_ld32(float* v) {
+    tc_wait_ld16(v);
+    tc_wait_ld16(v + 16);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int K0P, int DP>
+struct Cfg {
+    static constexpr int NB = K0P == 8 ? 3 : 2;    // W1 K-block stages
+    static constexpr int NS = K0P == 8 ? 3 : 2;    // layer-1 A-operand slots per track
+    static constexpr int ROWB0 = K0P * 4;          // layer-0 operand row pitch (SWIZZLE_32B / 64B)
+    static constexpr int A0_PART = TILE_M * ROWB0, A0_BYTES = 2 * A0_PART;
+    static constexpr int W0_CHUNK_PART = N0 * ROWB0, W0_CHUNK = 2 * W0_CHUNK_PART, W0_BYTES = MAX_NCH * W0_CHUNK;
+    static constexpr int W2_BYTES = TILE_N * DP * 4;
+    static constexpr int B_OFF = 0;
+    static constexpr int A1_OFF = B_OFF + NB * B_STAGE;
+    static constexpr int A0_OFF = A1_OFF + 2 * NS * A1_SLOT;
+    static constexpr int W0_OFF = A0_OFF + 2 * A0_BYTES;
+    static constexpr int W2_OFF = W0_OFF + 2 * W0_BYTES;
+    static constexpr int BAR_OFF = W2_OFF + 2 * W2_BYTES;
+    static constexpr int NBARS = 2 * NB + 4 * NS + 14;
+    static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
+    static constexpr int ALIGN_PAD = 512;
+};
+
+// ---- one-time images (global memory, L2 resident) -------------------------------------------
+// W1 image: [nkb][hi|lo][208 rows x 16 k] SWIZZLE_64B; column H0 carries b1.
+__global__ void prep_w1_kernel(const float* W1 /*[H1][H0]*/, const float* b1, int H0, int H1, int nkb, unsigned char* img) {
+    const int total = nkb * TILE_N * KB;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int kb = i / (TILE_N * KB), rem = i - kb * TILE_N * KB;
+        const int n = rem / KB, kk = rem - n * KB, k = kb * KB + kk;
+        float w = 0.f;
+        if (n < H1) w = k < H0 ? W1[(size_t)n * H0 + k] : (k == H0 ? b1[n] : 0.f);
+        float hi, lo;
+        split_tf32(w, hi, lo);
+        unsigned char* base = img + (size_t)kb * B_STAGE;
+        *reinterpret_cast<float*>(base + swz<64>(n, kk)) = hi;
+        *reinterpret_cast<float*>(base + B_PART + swz<64>(n, kk)) = lo;
+    }
+}
+// Per-particle layer-0 image: [P][chunk][hi|lo][32 rows x K0P]; row n < H0 is m0[p][n]*[W0[n][:], b0[n]],
+// row H0 is the unit vector of the bias column (the constant-1 hidden unit), the rest zero.
+template <int K0P>
+__global__ void prep_w0_kernel(const float* W0 /*[H0][K0]*/, const float* b0, const float* mask0 /*[P][H0]*/, int P,
+                               int H0, int K0, unsigned char* img) {
+    typedef Cfg<K0P, 4> C;
+    const int total = P * MAX_NCH * N0 * K0P;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int p = i / (MAX_NCH * N0 * K0P), rem = i - p * (MAX_NCH * N0 * K0P);
+        const int j = rem / (N0 * K0P), rem2 = rem - j * (N0 * K0P);
+        const int rr = rem2 / K0P, k = rem2 - rr * K0P, n = j * N0 + rr;
+        float w = 0.f;
+        if (n < H0) w = mask0[(size_t)p * H0 + n] * (k < K0 ? W0[(size_t)n * K0 + k] : (k == K0 ? b0[n] : 0.f));
+        else if (n == H0) w = k == K0 ? 1.f : 0.f;
+        float hi, lo;
+        split_tf32(w, hi, lo);
+        unsigned char* base = img + (size_t)p * C::W0_BYTES + (size_t)j * C::W0_CHUNK;
+        *reinterpret_cast<float*>(base + swz<C::ROWB0>(rr, k)) = hi;
+        *reinterpret_cast<float*>(base + C::W0_CHUNK_PART + swz<C::ROWB0>(rr, k)) = lo;
+    }
+}
+// Per-particle output weights: W2p[p][c][o] = m1[p][c] * W2[o][c]  (mean head only, o < D)
+__global__ void prep_w2_kernel(const float* W2 /*[2D][H1]*/, const float* mask1 /*[P][H1]*/, int P, int H1, int D, int DP,
+                               float* out) {
+    const int total = P * TILE_N * DP;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int p = i / (TILE_N * DP), rem = i - p * (TILE_N * DP);
+        const int c = rem / DP, o = rem - c * DP;
+        out[i] = (c < H1 && o < D) ? mask1[(size_t)p * H1 + c] * W2[(size_t)o * H1 + c] : 0.f;
+    }
+}
+
+struct Images {
+    const unsigned char* W1img;
+    const unsigned char* W0img;
+    const float* W2p;
+};
+
+template <int GEO, bool TAN>
+__global__ void __launch_bounds__(THREADS, 1)
+bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p, int nkb) {
+    typedef Geo<GEO> G;
+    constexpr int D = G::D, DA = G::DA, NNA = G::NNA, NANG = G::NANG, K0 = DA + G::NU;
+    constexpr int K0P = K0 + 1 <= 8 ? 8 : 16, DP = D <= 4 ? 4 : 8;
+    typedef Cfg<K0P, DP> C;
+    constexpr int NB = C::NB, NS = C::NS, ROWB0 = C::ROWB0;
+    constexpr int TD = TAN ? D + G::NU : 0, RPP = 1 + TD, PPW = 32 / RPP, NPART = 4 * PPW;
+    constexpr uint32_t IDESC1 = idesc_tf32(TILE_M, TILE_N), IDESC0 = idesc_tf32(TILE_M, N0);
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + C::ALIGN_PAD - 1) & ~(uintptr_t)(C::ALIGN_PAD - 1));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+    uint64_t* b_full = bars;                 // [NB]
+    uint64_t* b_empty = b_full + NB;         // [NB]
+    uint64_t* a1_full = b_empty + NB;        // [2][NS]
+    uint64_t* a1_empty = a1_full + 2 * NS;   // [2][NS]
+    uint64_t* acc0_full = a1_empty + 2 * NS; // [2]
+    uint64_t* acc0_empty = acc0_full + 2;
+    uint64_t* a0_full = acc0_empty + 2;
+    uint64_t* acc1_full = a0_full + 2;
+    uint64_t* acc1_empty = acc1_full + 2;
+    uint64_t* w0_full = acc1_empty + 2;
+    uint64_t* w2_full = w0_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBARS);
+
+    const BnnNet<float>& n = a.net;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int P = n.P;
+
+    // ---- tile schedule: a contiguous range of (particle, row-block) tiles per CTA; track t takes
+    // every other tile of the range.  Track 1 is `skew` K-blocks behind track 0 in the W1 stream.
+    const long long NT = (long long)P * tiles_p;
+    const long long T0 = NT * blockIdx.x / gridDim.x, T1 = NT * (blockIdx.x + 1) / gridDim.x;
+    const int cnt = (int)(T1 - T0);
+    const int ntl[2] = {(cnt + 1) / 2, cnt / 2};
+    const int skew = (nkb / 2) & ~1;
+    const int nch = (nkb + 1) / 2;
+    const uint32_t w0_bytes = (uint32_t)nch * C::W0_CHUNK;
+
+    if (tid == 0) {
+        for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 2 * NS; ++s) { mbar_init(&a1_full[s], 128); mbar_init(&a1_empty[s], 1); }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&acc0_full[t], 1);
+            mbar_init(&acc0_empty[t], 128);
+            mbar_init(&a0_full[t], 128);
+            mbar_init(&acc1_full[t], 1);
+            mbar_init(&acc1_empty[t], 128);
+            mbar_init(&w0_full[t], 1);
+            mbar_init(&w2_full[t], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 16) {
+        // ================= loader: W1 K-blocks, shared by both tracks =================
+        if (lane == 0) {
+            const long long len0 = (long long)ntl[0] * nkb, len1 = ntl[1] ? (long long)skew + (long long)ntl[1] * nkb : 0;
+            const long long nblk = len0 > len1 ? len0 : len1;
+            for (long long nb = 0; nb < nblk; ++nb) {
+                const int s = (int)(nb % NB), kb = (int)(nb % nkb);
+                mbar_wait(&b_empty[s], (uint32_t)((nb / NB) & 1) ^ 1);
+                mbar_expect_tx(&b_full[s], B_STAGE);
+                bulk_g2s(smem + C::B_OFF + s * B_STAGE, im.W1img + (size_t)kb * B_STAGE, B_STAGE, &b_full[s]);
+            }
+        }
+    } else if (warp == 17) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const long long len0 = (long long)ntl[0] * nkb, len1 = ntl[1] ? (long long)skew + (long long)ntl[1] * nkb : 0;
+            const long long nblk = len0 > len1 ? len0 : len1;
+            uint32_t l0cnt[2] = {0, 0}, w0loads[2] = {0, 0};
+            int curp[2] = {-1, -1};
+            // layer-0 MMA of chunk j of tile k on track t (first = first chunk of that tile)
+            auto issue_l0 = [&](int t, int k, int j, bool first) {
+                if (first) {
+                    const int p = (int)((T0 + 2 * k + t) / tiles_p);
+                    if (p != curp[t]) { mbar_wait(&w0_full[t], w0loads[t] & 1); ++w0loads[t]; curp[t] = p; }
+                    mbar_wait(&a0_full[t], (uint32_t)k & 1);
+                }
+                mbar_wait(&acc0_empty[t], (l0cnt[t] & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC0);
+                const uint32_t a0 = smem_u32(smem + C::A0_OFF + t * C::A0_BYTES);
+                const uint32_t b0 = smem_u32(smem + C::W0_OFF + t * C::W0_BYTES + j * C::W0_CHUNK);
+                const uint64_t ahi = make_desc<ROWB0>(a0), alo = make_desc<ROWB0>(a0 + C::A0_PART);
+                const uint64_t bhi = make_desc<ROWB0>(b0), blo = make_desc<ROWB0>(b0 + C::W0_CHUNK_PART);
+#pragma unroll
+                for (int ks = 0; ks < K0P / 8; ++ks) {
+                    const uint64_t o = (uint64_t)(ks * 2);
+                    tc_mma_tf32(d_tmem, ahi + o, bhi + o, IDESC0, ks != 0);
+                    tc_mma_tf32(d_tmem, alo + o, bhi + o, IDESC0, 1);
+                    tc_mma_tf32(d_tmem, ahi + o, blo + o, IDESC0, 1);
+                }
+                tc_commit(&acc0_full[t]);
+                ++l0cnt[t];
+            };
+            for (long long nb = 0; nb < nblk; ++nb) {
+                const int s = (int)(nb % NB), kb = (int)(nb % nkb);
+                bool bwaited = false;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const long long m = nb - (long long)t * skew;
+                    if (ntl[t] == 0 || m < 0 || m >= (long long)ntl[t] * nkb) continue;
+                    const int k = (int)(m / nkb), pos = (int)(m - (long long)k * nkb);
+                    if (m == 0) issue_l0(t, 0, kb >> 1, true);
+                    if ((kb & 1) == 0) {
+                        // chunk boundary: queue the NEXT chunk's layer-0 MMA behind the mid-stage's drain
+                        const int nk = kb + 1 < nkb ? 2 : 1;
+                        if (pos + nk < nkb) {
+                            int kb2 = kb + nk;
+                            if (kb2 >= nkb) kb2 -= nkb;
+                            issue_l0(t, k, kb2 >> 1, false);
+                        } else if (k + 1 < ntl[t]) {
+                            issue_l0(t, k + 1, (t * skew) >> 1, true);
+                        }
+                    }
+                    if (pos == 0) mbar_wait(&acc1_empty[t], ((uint32_t)k & 1) ^ 1);
+                    if (!bwaited) { mbar_wait(&b_full[s], (uint32_t)((nb / NB) & 1)); bwaited = true; }
+                    const int slot = (int)(m % NS);
+                    mbar_wait(&a1_full[t * NS + slot], (uint32_t)((m / NS) & 1));
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC1);
+                    const uint32_t aa = smem_u32(smem + C::A1_OFF + (t * NS + slot) * A1_SLOT);
+                    const uint32_t bb = smem_u32(smem + C::B_OFF + s * B_STAGE);
+                    const uint64_t ahi = make_desc<64>(aa), alo = make_desc<64>(aa + A1_PART);
+                    const uint64_t bhi = make_desc<64>(bb), blo = make_desc<64>(bb + B_PART);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {      // UMMA_K = 8 tf32 = 32 B -> +2 in the >>4 address field
+                        const uint64_t o = (uint64_t)(ks * 2);
+                        tc_mma_tf32(d_tmem, ahi + o, bhi + o, IDESC1, (pos | ks) != 0);
+                        tc_mma_tf32(d_tmem, alo + o, bhi + o, IDESC1, 1);
+                        tc_mma_tf32(d_tmem, ahi + o, blo + o, IDESC1, 1);
+                    }
+                    tc_commit(&a1_empty[t * NS + slot]);
+                    if (pos == nkb - 1) tc_commit(&acc1_full[t]);
+                }
+                tc_commit(&b_empty[s]);
+            }
+        }
+    } else {
+        // ================= worker teams: warps 0-7 epilogue (track 0, 1), warps 8-15 mid-stage =================
+        const int team = warp >> 2, t = team & 1;
+        const int r = tid & 127, w = r >> 5;                  // row of the tile = TMEM lane; w = lane quarter
+        const int ql = lane / RPP, d = lane - ql * RPP, q = w * PPW + ql;
+        const uint32_t primal_bit = 1u << (ql * RPP);
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(t * TM_TRACK);
+        const int nt = ntl[t];
+        if (nt == 0) goto done;
+        if (team >= 2) {
+            // ---------------- mid-stage: inputs -> A0, layer-0 accumulator -> A1 ----------------
+            unsigned char* A0 = smem + C::A0_OFF + t * C::A0_BYTES;
+            float xn[D], un = 0.f;
+            bool vn = false;
+            auto fetch = [&](int k) {      // row of tile k: particle p, group i -> global row i*P + p
+                const long long tau = T0 + 2 * k + t;
+                const int p = (int)(tau / tiles_p), l = (int)(tau - (long long)p * tiles_p);
+                const int i = l * NPART + q;
+                vn = ql < PPW && i < S;
+#pragma unroll
+                for (int e = 0; e < D; ++e) xn[e] = 0.f;
+                un = 0.f;
+                if (vn) {
+                    const float* xp = a.X + ((size_t)i * P + p) * D;
+                    if (D % 4 == 0) {
+#pragma unroll
+                        for (int e = 0; e < D; e += 4) *reinterpret_cast<float4*>(xn + e) = __ldg(reinterpret_cast<const float4*>(xp + e));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < D; e += 2) *reinterpret_cast<float2*>(xn + e) = __ldg(reinterpret_cast<const float2*>(xp + e));
+                    }
+                    un = __ldg(a.u + i);
+                }
+            };
+            auto write_a0 = [&]() {        // [norm(aug(x), u), 1] (primal) or its tangent along direction d-1
+                float row[K0P];
+#pragma unroll
+                for (int k = 0; k < K0P; ++k) row[k] = 0.f;
+                if (vn) {
+                    float in[K0], sc[K0];
+#pragma unroll
+                    for (int k = 0; k < K0; ++k) sc[k] = n.X_std_inv ? n.X_std_inv[k] : 1.f;
+#pragma unroll
+                    for (int i = 0; i < NNA; ++i) in[i] = xn[G::nonang(i)];
+#pragma unroll
+                    for (int i = 0; i < NANG; ++i) { in[NNA + 2 * i] = sinf(xn[G::ang(i)]); in[NNA + 2 * i + 1] = cosf(xn[G::ang(i)]); }
+                    in[DA] = un;
+                    if (!TAN || d == 0) {
+#pragma unroll
+                        for (int k = 0; k < K0; ++k) row[k] = (in[k] - (n.X_mean ? n.X_mean[k] : 0.f)) * sc[k];
+                        row[K0] = 1.f;
+                    } else {
+                        const int dir = d - 1;
+#pragma unroll
+                        for (int i = 0; i < NNA; ++i) if (dir == G::nonang(i)) row[i] = sc[i];
+#pragma unroll
+                        for (int i = 0; i < NANG; ++i) if (dir == G::ang(i)) {
+                            row[NNA + 2 * i] = in[NNA + 2 * i + 1] * sc[NNA + 2 * i];
+                            row[NNA + 2 * i + 1] = -in[NNA + 2 * i] * sc[NNA + 2 * i + 1];
+                        }
+                        if (dir == D) row[DA] = sc[DA];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < K0P / 4; ++c) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split_tf32(row[4 * c + e], hi[e], lo[e]);
+                    const uint32_t off = swz<ROWB0>(r, 4 * c);
+                    *reinterpret_cast<float4*>(A0 + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(A0 + C::A0_PART + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                fence_async_smem();
+                mbar_arrive(&a0_full[t]);
+            };
+            auto load_w0 = [&](int p) {
+                mbar_expect_tx(&w0_full[t], w0_bytes);
+                bulk_g2s(smem + C::W0_OFF + t * C::W0_BYTES, im.W0img + (size_t)p * C::W0_BYTES, w0_bytes, &w0_full[t]);
+            };
+            int curp = (int)((T0 + t) / tiles_p);
+            if (r == 0) load_w0(curp);
+            fetch(0);
+            write_a0();
+            uint32_t ci = 0, m = 0;
+            const int kb0 = t * skew;
+            for (int k = 0; k < nt; ++k) {
+                if (k + 1 < nt) fetch(k + 1);
+                for (int pos = 0; pos < nkb;) {
+                    int kb = kb0 + pos;
+                    if (kb >= nkb) kb -= nkb;
+                    const int nk = kb + 1 < nkb ? 2 : 1;
+                    float v[32];
+                    mbar_wait(&acc0_full[t], ci & 1);
+                    ++ci;
+                    tc_fence_after();
+                    tc_ld32(lane_taddr + TM_ACC0, v);
+                    tc_wait_ld32(v);
+                    tc_fence_before();
+                    mbar_arrive(&acc0_empty[t]);
+                    if (pos + nk >= nkb && k + 1 < nt) {
+                        // every layer-0 MMA of this tile has completed: A0 and the W0 image are free
+                        const int pn = (int)((T0 + 2 * (k + 1) + t) / tiles_p);
+                        if (pn != curp) { if (r == 0) load_w0(pn); curp = pn; }
+                        write_a0();
+                    }
+                    if (TAN) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const unsigned on = __ballot_sync(0xffffffffu, v[e] > 0.f);
+                            v[e] = (on & primal_bit) ? v[e] : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h < nk) {
+                            const uint32_t slot = m % NS;
+                            mbar_wait(&a1_empty[t * NS + slot], ((m / NS) & 1) ^ 1);
+                            unsigned char* A1 = smem + C::A1_OFF + (t * NS + slot) * A1_SLOT;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                float hi[4], lo[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) split_tf32(v[16 * h + 4 * c + e], hi[e], lo[e]);
+                                const uint32_t off = swz<64>(r, 4 * c);
+                                *reinterpret_cast<float4*>(A1 + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                                *reinterpret_cast<float4*>(A1 + A1_PART + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                            }
+                            fence_async_smem();
+                            mbar_arrive(&a1_full[t * NS + slot]);
+                            ++m;
+                        }
+                    }
+                    pos += nk;
+                }
+            }
+        } else {
+            // ---------------- epilogue: layer-1 accumulator -> ReLU -> output layer -> X', dX'/d(X,u) ----------------
+            const float* W2s = reinterpret_cast<const float*>(smem + C::W2_OFF + t * C::W2_BYTES);
+            int curp = -1;
+            uint32_t w2loads = 0;
+            for (int k = 0; k < nt; ++k) {
+                const long long tau = T0 + 2 * k + t;
+                const int p = (int)(tau / tiles_p), l = (int)(tau - (long long)p * tiles_p);
+                const int i = l * NPART + q;
+                const bool valid = ql < PPW && i < S;
+                const size_t g = (size_t)i * P + p;
+                if (p != curp) {
+                    named_bar_sync(1 + t, 128);      // every warp of the team is done with the old weights
+                    if (r == 0) {
+                        mbar_expect_tx(&w2_full[t], C::W2_BYTES);
+                        bulk_g2s(smem + C::W2_OFF + t * C::W2_BYTES, im.W2p + (size_t)p * TILE_N * DP, C::W2_BYTES, &w2_full[t]);
+                    }
+                    mbar_wait(&w2_full[t], w2loads & 1);
+                    ++w2loads;
+                    curp = p;
+                }
+                float x0[D];
+#pragma unroll
+                for (int o = 0; o < D; ++o) x0[o] = 0.f;
+                if (valid && (!TAN || d == 0)) {
+#pragma unroll
+                    for (int o = 0; o < D; ++o) x0[o] = __ldg(a.X + g * D + o);
+                }
+                float y[D];
+#pragma unroll
+                for (int o = 0; o < D; ++o) y[o] = 0.f;
+                mbar_wait(&acc1_full[t], (uint32_t)k & 1);
+                tc_fence_after();
+                float buf[2][16];
+                tc_ld16_nowait(lane_taddr + TM_ACC1, buf[0]);
+                tc_wait_ld16(buf[0]);
+#pragma unroll
+                for (int cb = 0; cb < TILE_N / 16; ++cb) {
+                    float* cur = buf[cb & 1];
+                    float* nxt = buf[(cb + 1) & 1];
+                    if (cb + 1 < TILE_N / 16) tc_ld16_nowait(lane_taddr + TM_ACC1 + 16 * (cb + 1), nxt);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        float vv;
+                        if (TAN) {
+                            const unsigned on = __ballot_sync(0xffffffffu, cur[e] > 0.f);
+                            vv = (on & primal_bit) ? cur[e] : 0.f;
+                        } else {
+                            vv = fmaxf(cur[e], 0.f);
+                        }
+                        float w2[DP];
+#pragma unroll
+                        for (int o4 = 0; o4 < DP / 4; ++o4)
+                            *reinterpret_cast<float4*>(w2 + 4 * o4) = *reinterpret_cast<const float4*>(W2s + (16 * cb + e) * DP + 4 * o4);
+#pragma unroll
+                        for (int o = 0; o < D; ++o) y[o] += vv * w2[o];
+                    }
+                    if (cb + 1 < TILE_N / 16) tc_wait_ld16(nxt);
+                }
+                tc_fence_before();
+                mbar_arrive(&acc1_empty[t]);
+                if (valid) {
+#pragma unroll
+                    for (int o = 0; o < D; ++o) {
+                        const float sd = n.dX_std ? n.dX_std[o] : 1.f, mn = n.dX_mean ? n.dX_mean[o] : 0.f;
+                        if (!TAN || d == 0) a.Xn[g * D + o] = x0[o] + ((y[o] + n.b2[o]) * sd + mn);
+                        else a.Jp[(g * D + o) * TD + (d - 1)] = ((d - 1) == o ? 1.f : 0.f) + y[o] * sd;
+                    }
+                }
+            }
+        }
+    }
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
+}  // namespace tc2
+}  // namespace pddp

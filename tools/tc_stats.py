@@ -1,9 +1,13 @@
-import sys, torch
-sys.path.insert(0, '/root/repo')
+"""fp32 (tcgen05 or, with PDDP_FORCE_SIMT=1, SIMT) against fp64 on the same synthetic problems:
+error quantiles per output.  usage: python tools/tc_stats.py [B] [N_cartpole] [N_double]"""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 37
+NS = (int(sys.argv[2]) if len(sys.argv) > 2 else 30, int(sys.argv[3]) if len(sys.argv) > 3 else 12)
 from pddp_b200.solver import BatchedSolver, BNNDynamics, QRCostConstants
-for workload, N in (("cartpole_bnn_b4096", 30), ("double_cartpole_bnn_fullcov_b1024", 12)):
-    w = dict(bench.WORKLOADS[workload], B=37, N=N)
+for workload, N in (("cartpole_bnn_b4096", NS[0]), ("double_cartpole_bnn_fullcov_b1024", NS[1])):
+    w = dict(bench.WORKLOADS[workload], B=B, N=N)
     geo, D, ang, nonang = bench.GEOMETRY[w["problem"]]
     W, b, masks, eps0 = bench.synth_bnn(w["problem"], w["P"], w["hidden"], seed=3)
     cost = QRCostConstants(*bench.cost_constants(w["problem"]))
@@ -15,7 +19,8 @@ for workload, N in (("cartpole_bnn_b4096", 30), ("double_cartpole_bnn_fullcov_b1
         s.mu.fill_(1.0)
         s.linearize(); s.backward(); s.rollout()
         torch.cuda.synchronize()
-        out[dtype] = {n: s.matrices(n).double().cpu() for n in ("Z", "F_z", "F_u", "k", "K")}
+        out[dtype] = {n: s.matrices(n).double().cpu() for n in ("Z", "F_z", "F_u", "k", "K", "Z_new", "U_new")}
+        out[dtype]["J"] = s.J_all.double().cpu()
     for n in out[torch.float64]:
         a, bb = out[torch.float32][n], out[torch.float64][n]
         e = (a - bb).abs().flatten(); sc = bb.abs().max()

@@ -230,6 +230,8 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
     const int skew = (nkb / 2) & ~1;
     const int nch = (nkb + 1) / 2;
     const uint32_t w0_bytes = (uint32_t)nch * C::W0_CHUNK;
+    const int len0 = ntl[0] * nkb, len1 = ntl[1] ? skew + ntl[1] * nkb : 0;
+    const int nblk = len0 > len1 ? len0 : len1;          // W1 K-blocks this CTA streams
 
     if (tid == 0) {
         for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -257,20 +259,18 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
     if (warp == 16) {
         // ================= loader: W1 K-blocks, shared by both tracks =================
         if (lane == 0) {
-            const long long len0 = (long long)ntl[0] * nkb, len1 = ntl[1] ? (long long)skew + (long long)ntl[1] * nkb : 0;
-            const long long nblk = len0 > len1 ? len0 : len1;
-            for (long long nb = 0; nb < nblk; ++nb) {
-                const int s = (int)(nb % NB), kb = (int)(nb % nkb);
-                mbar_wait(&b_empty[s], (uint32_t)((nb / NB) & 1) ^ 1);
+            uint32_t s = 0, ph = 1, kb = 0;
+            for (int nb = 0; nb < nblk; ++nb) {
+                mbar_wait(&b_empty[s], ph);
                 mbar_expect_tx(&b_full[s], B_STAGE);
                 bulk_g2s(smem + C::B_OFF + s * B_STAGE, im.W1img + (size_t)kb * B_STAGE, B_STAGE, &b_full[s]);
+                if (++s == NB) { s = 0; ph ^= 1; }
+                if (++kb == (uint32_t)nkb) kb = 0;
             }
         }
     } else if (warp == 17) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const long long len0 = (long long)ntl[0] * nkb, len1 = ntl[1] ? (long long)skew + (long long)ntl[1] * nkb : 0;
-            const long long nblk = len0 > len1 ? len0 : len1;
             uint32_t l0cnt[2] = {0, 0}, w0loads[2] = {0, 0};
             int curp[2] = {-1, -1};
             // layer-0 MMA of chunk j of tile k on track t (first = first chunk of that tile)
@@ -297,15 +297,17 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                 tc_commit(&acc0_full[t]);
                 ++l0cnt[t];
             };
-            for (long long nb = 0; nb < nblk; ++nb) {
-                const int s = (int)(nb % NB), kb = (int)(nb % nkb);
+            uint32_t s = 0, bph = 0;
+            int kb = 0;
+            int tk[2] = {0, 0}, tpos[2] = {0, 0};            // per track: tile index, position in the tile
+            uint32_t tslot[2] = {0, 0}, tph[2] = {0, 0};     // per track: A1 slot and its full-barrier parity
+            for (int nb = 0; nb < nblk; ++nb) {
                 bool bwaited = false;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    const long long m = nb - (long long)t * skew;
-                    if (ntl[t] == 0 || m < 0 || m >= (long long)ntl[t] * nkb) continue;
-                    const int k = (int)(m / nkb), pos = (int)(m - (long long)k * nkb);
-                    if (m == 0) issue_l0(t, 0, kb >> 1, true);
+                    if (nb < t * skew || tk[t] >= ntl[t]) continue;
+                    const int k = tk[t], pos = tpos[t];
+                    if (k == 0 && pos == 0) issue_l0(t, 0, kb >> 1, true);
                     if ((kb & 1) == 0) {
                         // chunk boundary: queue the NEXT chunk's layer-0 MMA behind the mid-stage's drain
                         const int nk = kb + 1 < nkb ? 2 : 1;
@@ -318,9 +320,9 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                         }
                     }
                     if (pos == 0) mbar_wait(&acc1_empty[t], ((uint32_t)k & 1) ^ 1);
-                    if (!bwaited) { mbar_wait(&b_full[s], (uint32_t)((nb / NB) & 1)); bwaited = true; }
-                    const int slot = (int)(m % NS);
-                    mbar_wait(&a1_full[t * NS + slot], (uint32_t)((m / NS) & 1));
+                    if (!bwaited) { mbar_wait(&b_full[s], bph); bwaited = true; }
+                    const uint32_t slot = tslot[t];
+                    mbar_wait(&a1_full[t * NS + slot], tph[t]);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC1);
                     const uint32_t aa = smem_u32(smem + C::A1_OFF + (t * NS + slot) * A1_SLOT);
@@ -336,8 +338,12 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                     }
                     tc_commit(&a1_empty[t * NS + slot]);
                     if (pos == nkb - 1) tc_commit(&acc1_full[t]);
+                    if (++tslot[t] == NS) { tslot[t] = 0; tph[t] ^= 1; }
+                    if (++tpos[t] == nkb) { tpos[t] = 0; ++tk[t]; }
                 }
                 tc_commit(&b_empty[s]);
+                if (++s == NB) { s = 0; bph ^= 1; }
+                if (++kb == nkb) kb = 0;
             }
         }
     } else {
@@ -423,7 +429,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
             if (r == 0) load_w0(curp);
             fetch(0);
             write_a0();
-            uint32_t ci = 0, m = 0;
+            uint32_t ci = 0, slot = 0, sph = 1;
             const int kb0 = t * skew;
             for (int k = 0; k < nt; ++k) {
                 if (k + 1 < nt) fetch(k + 1);
@@ -458,8 +464,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         if (h < nk) {
-                            const uint32_t slot = m % NS;
-                            mbar_wait(&a1_empty[t * NS + slot], ((m / NS) & 1) ^ 1);
+                            mbar_wait(&a1_empty[t * NS + slot], sph);
                             unsigned char* A1 = smem + C::A1_OFF + (t * NS + slot) * A1_SLOT;
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
@@ -472,7 +477,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                             }
                             fence_async_smem();
                             mbar_arrive(&a1_full[t * NS + slot]);
-                            ++m;
+                            if (++slot == NS) { slot = 0; sph ^= 1; }
                         }
                     }
                     pos += nk;

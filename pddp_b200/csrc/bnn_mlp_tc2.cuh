@@ -19,8 +19,8 @@
 //   * two independent tile "tracks" per CTA consume the same streamed W1 K-block (16 wide,
 //     SWIZZLE_64B, hi|lo TF32 parts): half the L2->smem traffic per row.  Track 1 runs half a
 //     tile behind track 0, so one track's epilogue/input phase is covered by the other's MMAs;
-//   * warp roles (18 warps): 4 epilogue + 4 mid-stage warps per track, 1 bulk-copy loader, 1 MMA
-//     issuer.  mid-stage = tcgen05.ld of the layer-0 accumulator, ReLU (tangent rows gated by
+//   * warp roles (19 warps): 4 epilogue + 4 mid-stage warps and 1 MMA-issuer thread per track,
+//     1 bulk-copy loader.  mid-stage = tcgen05.ld of the layer-0 accumulator, ReLU (tangent rows gated by
 //     their primal row via __ballot_sync), hi/lo split, st.shared into the UMMA K-major layout.
 //
 // TMEM (512 columns): track t owns columns [256t, 256t+208) for the layer-1 accumulator and
@@ -48,7 +48,7 @@ constexpr int B_PART = TILE_N * 64;    // one hi or lo part of a W1 K-block: 208
 constexpr int B_STAGE = 2 * B_PART;    // 26 624 B
 constexpr int A1_PART = TILE_M * 64;   // 128 rows x 16 tf32
 constexpr int A1_SLOT = 2 * A1_PART;   // 16 384 B
-constexpr int THREADS = 18 * 32;
+constexpr int THREADS = 19 * 32;
 constexpr int TM_ACC1 = 0, TM_ACC0 = 208, TM_TRACK = 256;
 
 // byte offset of element (row, kk) in a K-major tile whose rows are ROWB bytes (32 / 64 / 128 =
@@ -234,7 +234,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
     const int nblk = len0 > len1 ? len0 : len1;          // W1 K-blocks this CTA streams
 
     if (tid == 0) {
-        for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2); }   // both tracks release a W1 stage
         for (int s = 0; s < 2 * NS; ++s) { mbar_init(&a1_full[s], 128); mbar_init(&a1_empty[s], 1); }
         for (int t = 0; t < 2; ++t) {
             mbar_init(&acc0_full[t], 1);
@@ -256,7 +256,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 16) {
+    if (warp == 18) {
         // ================= loader: W1 K-blocks, shared by both tracks =================
         if (lane == 0) {
             uint32_t s = 0, ph = 1, kb = 0;
@@ -268,19 +268,21 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                 if (++kb == (uint32_t)nkb) kb = 0;
             }
         }
-    } else if (warp == 17) {
-        // ================= MMA issuer =================
+    } else if (warp >= 16) {
+        // ================= MMA issuers: one thread per track (a track that waits for its epilogue
+        // or its mid-stage does not hold the other one up; they drift at most NB W1 stages apart) ====
         if (lane == 0) {
-            uint32_t l0cnt[2] = {0, 0}, w0loads[2] = {0, 0};
-            int curp[2] = {-1, -1};
-            // layer-0 MMA of chunk j of tile k on track t (first = first chunk of that tile)
-            auto issue_l0 = [&](int t, int k, int j, bool first) {
+            const int t = warp - 16;
+            uint32_t l0cnt = 0, w0loads = 0;
+            int curp = -1;
+            // layer-0 MMA of chunk starting at K-block kbc of tile k (first = first chunk of that tile)
+            auto issue_l0 = [&](int k, int j, bool first) {
                 if (first) {
                     const int p = (int)((T0 + 2 * k + t) / tiles_p);
-                    if (p != curp[t]) { mbar_wait(&w0_full[t], w0loads[t] & 1); ++w0loads[t]; curp[t] = p; }
+                    if (p != curp) { mbar_wait(&w0_full[t], w0loads & 1); ++w0loads; curp = p; }
                     mbar_wait(&a0_full[t], (uint32_t)k & 1);
                 }
-                mbar_wait(&acc0_empty[t], (l0cnt[t] & 1) ^ 1);
+                mbar_wait(&acc0_empty[t], (l0cnt & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC0);
                 const uint32_t a0 = smem_u32(smem + C::A0_OFF + t * C::A0_BYTES);
@@ -295,34 +297,29 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                     tc_mma_tf32(d_tmem, ahi + o, blo + o, IDESC0, 1);
                 }
                 tc_commit(&acc0_full[t]);
-                ++l0cnt[t];
+                ++l0cnt;
             };
-            uint32_t s = 0, bph = 0;
-            int kb = 0;
-            int tk[2] = {0, 0}, tpos[2] = {0, 0};            // per track: tile index, position in the tile
-            uint32_t tslot[2] = {0, 0}, tph[2] = {0, 0};     // per track: A1 slot and its full-barrier parity
+            uint32_t s = 0, bph = 0, slot = 0, sph = 0;
+            int kb = 0, k = 0, pos = 0;
             for (int nb = 0; nb < nblk; ++nb) {
-                bool bwaited = false;
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    if (nb < t * skew || tk[t] >= ntl[t]) continue;
-                    const int k = tk[t], pos = tpos[t];
-                    if (k == 0 && pos == 0) issue_l0(t, 0, kb >> 1, true);
+                mbar_wait(&b_full[s], bph);
+                if (nb < t * skew || k >= ntl[t]) {
+                    mbar_arrive(&b_empty[s]);               // this track does not use the block
+                } else {
+                    if (k == 0 && pos == 0) issue_l0(0, kb >> 1, true);
                     if ((kb & 1) == 0) {
                         // chunk boundary: queue the NEXT chunk's layer-0 MMA behind the mid-stage's drain
                         const int nk = kb + 1 < nkb ? 2 : 1;
                         if (pos + nk < nkb) {
                             int kb2 = kb + nk;
                             if (kb2 >= nkb) kb2 -= nkb;
-                            issue_l0(t, k, kb2 >> 1, false);
+                            issue_l0(k, kb2 >> 1, false);
                         } else if (k + 1 < ntl[t]) {
-                            issue_l0(t, k + 1, (t * skew) >> 1, true);
+                            issue_l0(k + 1, (t * skew) >> 1, true);
                         }
                     }
                     if (pos == 0) mbar_wait(&acc1_empty[t], ((uint32_t)k & 1) ^ 1);
-                    if (!bwaited) { mbar_wait(&b_full[s], bph); bwaited = true; }
-                    const uint32_t slot = tslot[t];
-                    mbar_wait(&a1_full[t * NS + slot], tph[t]);
+                    mbar_wait(&a1_full[t * NS + slot], sph);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC1);
                     const uint32_t aa = smem_u32(smem + C::A1_OFF + (t * NS + slot) * A1_SLOT);
@@ -337,11 +334,11 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                         tc_mma_tf32(d_tmem, ahi + o, blo + o, IDESC1, 1);
                     }
                     tc_commit(&a1_empty[t * NS + slot]);
+                    tc_commit(&b_empty[s]);
                     if (pos == nkb - 1) tc_commit(&acc1_full[t]);
-                    if (++tslot[t] == NS) { tslot[t] = 0; tph[t] ^= 1; }
-                    if (++tpos[t] == nkb) { tpos[t] = 0; ++tk[t]; }
+                    if (++slot == NS) { slot = 0; sph ^= 1; }
+                    if (++pos == nkb) { pos = 0; ++k; }
                 }
-                tc_commit(&b_empty[s]);
                 if (++s == NB) { s = 0; bph ^= 1; }
                 if (++kb == nkb) kb = 0;
             }
@@ -516,31 +513,36 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                 for (int o = 0; o < D; ++o) y[o] = 0.f;
                 mbar_wait(&acc1_full[t], (uint32_t)k & 1);
                 tc_fence_after();
-                float buf[2][16];
-                tc_ld16_nowait(lane_taddr + TM_ACC1, buf[0]);
-                tc_wait_ld16(buf[0]);
+                // the accumulator is drained in batches of 64 columns: one TMEM round trip per batch
 #pragma unroll
-                for (int cb = 0; cb < TILE_N / 16; ++cb) {
-                    float* cur = buf[cb & 1];
-                    float* nxt = buf[(cb + 1) & 1];
-                    if (cb + 1 < TILE_N / 16) tc_ld16_nowait(lane_taddr + TM_ACC1 + 16 * (cb + 1), nxt);
+                for (int c0 = 0; c0 < TILE_N; c0 += 64) {
+                    constexpr int NQ_MAX = 4;
+                    float buf[16 * NQ_MAX];
+                    const int nq = (TILE_N - c0) / 16 < NQ_MAX ? (TILE_N - c0) / 16 : NQ_MAX;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        float vv;
-                        if (TAN) {
-                            const unsigned on = __ballot_sync(0xffffffffu, cur[e] > 0.f);
-                            vv = (on & primal_bit) ? cur[e] : 0.f;
-                        } else {
-                            vv = fmaxf(cur[e], 0.f);
+                    for (int qd = 0; qd < NQ_MAX; ++qd)
+                        if (qd < nq) tc_ld16_nowait(lane_taddr + TM_ACC1 + c0 + 16 * qd, buf + 16 * qd);
+#pragma unroll
+                    for (int qd = 0; qd < NQ_MAX; ++qd)
+                        if (qd < nq) tc_wait_ld16(buf + 16 * qd);
+#pragma unroll
+                    for (int e = 0; e < 16 * NQ_MAX; ++e) {
+                        if (e < 16 * nq) {
+                            float vv;
+                            if (TAN) {
+                                const unsigned on = __ballot_sync(0xffffffffu, buf[e] > 0.f);
+                                vv = (on & primal_bit) ? buf[e] : 0.f;
+                            } else {
+                                vv = fmaxf(buf[e], 0.f);
+                            }
+                            float w2[DP];
+#pragma unroll
+                            for (int o4 = 0; o4 < DP / 4; ++o4)
+                                *reinterpret_cast<float4*>(w2 + 4 * o4) = *reinterpret_cast<const float4*>(W2s + (c0 + e) * DP + 4 * o4);
+#pragma unroll
+                            for (int o = 0; o < D; ++o) y[o] += vv * w2[o];
                         }
-                        float w2[DP];
-#pragma unroll
-                        for (int o4 = 0; o4 < DP / 4; ++o4)
-                            *reinterpret_cast<float4*>(w2 + 4 * o4) = *reinterpret_cast<const float4*>(W2s + (16 * cb + e) * DP + 4 * o4);
-#pragma unroll
-                        for (int o = 0; o < D; ++o) y[o] += vv * w2[o];
                     }
-                    if (cb + 1 < TILE_N / 16) tc_wait_ld16(nxt);
                 }
                 tc_fence_before();
                 mbar_arrive(&acc1_empty[t]);

@@ -27,6 +27,7 @@
 // [256t+208, 256t+240) for the layer-0 chunk.
 #pragma once
 #include "bnn_mlp_tc.cuh"
+#include <cuda_bf16.h>
 
 namespace pddp {
 namespace tc2 {
@@ -44,9 +45,13 @@ using tc::tc_fence_before;
 using tc::tc_mma_tf32;
 
 constexpr int TILE_M = 128, TILE_N = 208, KB = 16, MAX_NKB = 13, MAX_NCH = 7, N0 = 32;
-constexpr int B_PART = TILE_N * 64;    // one hi or lo part of a W1 K-block: 208 rows x 16 tf32
+// Layer 1 computes a*b ~ a_hi*b_hi (TF32 x TF32) + [a_lo | a_hi] * [b_hi | b_lo] (BF16, K = 32): the two
+// cross terms are 2^-11 of the product, so 8-bit operands keep them to ~2^-20 -- fp32-class
+// accuracy for two tensor-core passes instead of the three of 3xTF32, and a third less operand
+// traffic from shared memory (the kernel is bound by the shared-memory data pipe, profiles/).
+constexpr int B_PART = TILE_N * 64;    // W1 K-block, part 0: 208 rows x 16 tf32 (hi); part 1: 208 rows x 32 bf16 [hi | lo]
 constexpr int B_STAGE = 2 * B_PART;    // 26 624 B
-constexpr int A1_PART = TILE_M * 64;   // 128 rows x 16 tf32
+constexpr int A1_PART = TILE_M * 64;   // part 0: 128 rows x 16 tf32 (hi); part 1: 128 rows x 32 bf16 [lo | hi]
 constexpr int A1_SLOT = 2 * A1_PART;   // 16 384 B
 constexpr int THREADS = 19 * 32;
 constexpr int TM_ACC1 = 0, TM_ACC0 = 208, TM_TRACK = 256;
@@ -79,6 +84,33 @@ constexpr uint32_t idesc_tf32(int M, int N) {
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
     lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
+}
+
+// two floats -> packed bf16x2 (a in the low half = lower address)
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float x, float y, float z, float w) {
+    sts128(addr, __float_as_uint(x), __float_as_uint(y), __float_as_uint(z), __float_as_uint(w));
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate) : "memory");
+}
+constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
@@ -145,11 +177,14 @@ __global__ void prep_w1_kernel(const float* W1 /*[H1][H0]*/, const float* b1, in
         const int n = rem / KB, kk = rem - n * KB, k = kb * KB + kk;
         float w = 0.f;
         if (n < H1) w = k < H0 ? W1[(size_t)n * H0 + k] : (k == H0 ? b1[n] : 0.f);
-        float hi, lo;
-        split_tf32(w, hi, lo);
+        const float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);
         unsigned char* base = img + (size_t)kb * B_STAGE;
         *reinterpret_cast<float*>(base + swz<64>(n, kk)) = hi;
-        *reinterpret_cast<float*>(base + B_PART + swz<64>(n, kk)) = lo;
+        // bf16 part: element kk of [hi | lo] sits at 2-byte index kk (hi) or 16 + kk (lo) of the 64-byte row
+        unsigned char* b2 = base + B_PART + (n >> 3) * 512 + (n & 7) * 64;
+        const int sw = (n >> 1) & 3;
+        *reinterpret_cast<__nv_bfloat16*>(b2 + ((((kk >> 3)) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(w);
+        *reinterpret_cast<__nv_bfloat16*>(b2 + (((2 + (kk >> 3)) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(w - hi);
     }
 }
 // Per-particle layer-0 image: [P][chunk][hi|lo][32 rows x K0P]; row n < H0 is m0[p][n]*[W0[n][:], b0[n]],
@@ -199,7 +234,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
     typedef Cfg<K0P, DP> C;
     constexpr int NB = C::NB, NS = C::NS, ROWB0 = C::ROWB0;
     constexpr int TD = TAN ? D + G::NU : 0, RPP = 1 + TD, PPW = 32 / RPP, NPART = 4 * PPW;
-    constexpr uint32_t IDESC1 = idesc_tf32(TILE_M, TILE_N), IDESC0 = idesc_tf32(TILE_M, N0);
+    constexpr uint32_t IDESC1 = idesc_tf32(TILE_M, TILE_N), IDESC1B = idesc_bf16(TILE_M, TILE_N), IDESC0 = idesc_tf32(TILE_M, N0);
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + C::ALIGN_PAD - 1) & ~(uintptr_t)(C::ALIGN_PAD - 1));
@@ -324,15 +359,13 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                     const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC1);
                     const uint32_t aa = smem_u32(smem + C::A1_OFF + (t * NS + slot) * A1_SLOT);
                     const uint32_t bb = smem_u32(smem + C::B_OFF + s * B_STAGE);
-                    const uint64_t ahi = make_desc<64>(aa), alo = make_desc<64>(aa + A1_PART);
-                    const uint64_t bhi = make_desc<64>(bb), blo = make_desc<64>(bb + B_PART);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {      // UMMA_K = 8 tf32 = 32 B -> +2 in the >>4 address field
-                        const uint64_t o = (uint64_t)(ks * 2);
-                        tc_mma_tf32(d_tmem, ahi + o, bhi + o, IDESC1, (pos | ks) != 0);
-                        tc_mma_tf32(d_tmem, alo + o, bhi + o, IDESC1, 1);
-                        tc_mma_tf32(d_tmem, ahi + o, blo + o, IDESC1, 1);
-                    }
+                    const uint64_t a32 = make_desc<64>(aa), a16 = make_desc<64>(aa + A1_PART);
+                    const uint64_t b32 = make_desc<64>(bb), b16 = make_desc<64>(bb + B_PART);
+                    // one UMMA K-step = 32 B of a row (8 tf32 / 16 bf16) -> +2 in the >>4 address field
+                    tc_mma_tf32(d_tmem, a32, b32, IDESC1, pos != 0);
+                    tc_mma_tf32(d_tmem, a32 + 2, b32 + 2, IDESC1, 1);
+                    tc_mma_bf16(d_tmem, a16, b16, IDESC1B, 1);          // a_lo * b_hi
+                    tc_mma_bf16(d_tmem, a16 + 2, b16 + 2, IDESC1B, 1);  // a_hi * b_lo
                     tc_commit(&a1_empty[t * NS + slot]);
                     tc_commit(&b_empty[s]);
                     if (pos == nkb - 1) tc_commit(&acc1_full[t]);
@@ -355,6 +388,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
         if (team >= 2) {
             // ---------------- mid-stage: inputs -> A0, layer-0 accumulator -> A1 ----------------
             unsigned char* A0 = smem + C::A0_OFF + t * C::A0_BYTES;
+            const uint32_t row_off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64), row_sw = (uint32_t)((r >> 1) & 3);   // SWIZZLE_64B row
             float xn[D], un = 0.f;
             bool vn = false;
             auto fetch = [&](int k) {      // row of tile k: particle p, group i -> global row i*P + p
@@ -412,8 +446,8 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
 #pragma unroll
                     for (int e = 0; e < 4; ++e) split_tf32(row[4 * c + e], hi[e], lo[e]);
                     const uint32_t off = swz<ROWB0>(r, 4 * c);
-                    *reinterpret_cast<float4*>(A0 + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(A0 + C::A0_PART + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    sts128f(smem_u32(A0) + off, hi[0], hi[1], hi[2], hi[3]);
+                    sts128f(smem_u32(A0) + C::A0_PART + off, lo[0], lo[1], lo[2], lo[3]);
                 }
                 fence_async_smem();
                 mbar_arrive(&a0_full[t]);
@@ -462,15 +496,24 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                     for (int h = 0; h < 2; ++h) {
                         if (h < nk) {
                             mbar_wait(&a1_empty[t * NS + slot], sph);
-                            unsigned char* A1 = smem + C::A1_OFF + (t * NS + slot) * A1_SLOT;
+                            const uint32_t A1 = smem_u32(smem + C::A1_OFF + (t * NS + slot) * A1_SLOT) + row_off;
+                            float hi[16], lo[16];
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                float hi[4], lo[4];
+                            for (int e = 0; e < 16; ++e) {
+                                hi[e] = __uint_as_float((__float_as_uint(v[16 * h + e]) + 0x1000u) & 0xFFFFE000u);
+                                lo[e] = v[16 * h + e] - hi[e];
+                            }
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) split_tf32(v[16 * h + 4 * c + e], hi[e], lo[e]);
-                                const uint32_t off = swz<64>(r, 4 * c);
-                                *reinterpret_cast<float4*>(A1 + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                                *reinterpret_cast<float4*>(A1 + A1_PART + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                            for (int c = 0; c < 4; ++c)      // part 0: hi as tf32
+                                sts128f(A1 + ((c ^ row_sw) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {    // part 1: [lo | hi] as bf16, 8 per 16-byte chunk
+                                sts128(A1 + A1_PART + ((c ^ row_sw) << 4), pack_bf16(lo[8 * c], lo[8 * c + 1]),
+                                       pack_bf16(lo[8 * c + 2], lo[8 * c + 3]), pack_bf16(lo[8 * c + 4], lo[8 * c + 5]),
+                                       pack_bf16(lo[8 * c + 6], lo[8 * c + 7]));
+                                sts128(A1 + A1_PART + (((2 + c) ^ row_sw) << 4), pack_bf16(hi[8 * c], hi[8 * c + 1]),
+                                       pack_bf16(hi[8 * c + 2], hi[8 * c + 3]), pack_bf16(hi[8 * c + 4], hi[8 * c + 5]),
+                                       pack_bf16(hi[8 * c + 6], hi[8 * c + 7]));
                             }
                             fence_async_smem();
                             mbar_arrive(&a1_full[t * NS + slot]);
@@ -482,7 +525,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
             }
         } else {
             // ---------------- epilogue: layer-1 accumulator -> ReLU -> output layer -> X', dX'/d(X,u) ----------------
-            const float* W2s = reinterpret_cast<const float*>(smem + C::W2_OFF + t * C::W2_BYTES);
+            const uint32_t W2s = smem_u32(smem + C::W2_OFF + t * C::W2_BYTES);
             int curp = -1;
             uint32_t w2loads = 0;
             for (int k = 0; k < nt; ++k) {
@@ -538,7 +581,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                             float w2[DP];
 #pragma unroll
                             for (int o4 = 0; o4 < DP / 4; ++o4)
-                                *reinterpret_cast<float4*>(w2 + 4 * o4) = *reinterpret_cast<const float4*>(W2s + (c0 + e) * DP + 4 * o4);
+                                *reinterpret_cast<float4*>(w2 + 4 * o4) = lds128f(W2s + (uint32_t)(((c0 + e) * DP + 4 * o4) * 4));
 #pragma unroll
                             for (int o = 0; o < D; ++o) y[o] += vv * w2[o];
                         }

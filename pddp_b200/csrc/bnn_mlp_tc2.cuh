@@ -19,8 +19,8 @@
 //   * two independent tile "tracks" per CTA consume the same streamed W1 K-block (16 wide,
 //     SWIZZLE_64B, hi|lo TF32 parts): half the L2->smem traffic per row.  Track 1 runs half a
 //     tile behind track 0, so one track's epilogue/input phase is covered by the other's MMAs;
-//   * warp roles (19 warps): 4 epilogue + 4 mid-stage warps and 1 MMA-issuer thread per track,
-//     1 bulk-copy loader.  mid-stage = tcgen05.ld of the layer-0 accumulator, ReLU (tangent rows gated by
+//   * warp roles (20 warps): per track 4 epilogue + 4 mid-stage warps and one layer-1 MMA-issuer
+//     thread; one polling layer-0 issuer thread for both tracks; 1 bulk-copy loader.  mid-stage = tcgen05.ld of the layer-0 accumulator, ReLU (tangent rows gated by
 //     their primal row via __ballot_sync), hi/lo split, st.shared into the UMMA K-major layout.
 //
 // TMEM (512 columns): track t owns columns [256t, 256t+208) for the layer-1 accumulator and
@@ -53,7 +53,7 @@ constexpr int B_PART = TILE_N * 64;    // W1 K-block, part 0: 208 rows x 16 tf32
 constexpr int B_STAGE = 2 * B_PART;    // 26 624 B
 constexpr int A1_PART = TILE_M * 64;   // part 0: 128 rows x 16 tf32 (hi); part 1: 128 rows x 32 bf16 [lo | hi]
 constexpr int A1_SLOT = 2 * A1_PART;   // 16 384 B
-constexpr int THREADS = 19 * 32;
+constexpr int THREADS = 20 * 32;
 constexpr int TM_ACC1 = 0, TM_ACC0 = 208, TM_TRACK = 256;
 
 // byte offset of element (row, kk) in a K-major tile whose rows are ROWB bytes (32 / 64 / 128 =
@@ -144,6 +144,14 @@ __device__ __forceinline__ void tc_wait_ld16(float* v) {
 __device__ __forceinline__ void tc_wait_ld32(float* v) {
     tc_wait_ld16(v);
     tc_wait_ld16(v + 16);
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -303,37 +311,56 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                 if (++kb == (uint32_t)nkb) kb = 0;
             }
         }
+    } else if (warp == 19) {
+        // ================= layer-0 issuer (one thread, both tracks, polling): chunk c+1 of a track is
+        // issued the moment its mid-stage has drained chunk c, independent of where layer 1 stands ====
+        if (lane == 0) {
+            uint32_t l0cnt[2] = {0, 0}, w0loads[2] = {0, 0};
+            int curp[2] = {-1, -1}, k[2] = {0, 0}, pos[2] = {0, 0};
+            bool fresh[2] = {true, true};          // next chunk is the first of its tile
+            while (k[0] < ntl[0] || k[1] < ntl[1]) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (k[t] >= ntl[t]) continue;
+                    if (fresh[t]) {
+                        const int p = (int)((T0 + 2 * k[t] + t) / tiles_p);
+                        if (p != curp[t]) {
+                            if (!mbar_test(&w0_full[t], w0loads[t] & 1)) continue;
+                            ++w0loads[t];
+                            curp[t] = p;
+                        }
+                        if (!mbar_test(&a0_full[t], (uint32_t)k[t] & 1)) continue;
+                        fresh[t] = false;
+                    }
+                    if (!mbar_test(&acc0_empty[t], (l0cnt[t] & 1) ^ 1)) continue;
+                    tc_fence_after();
+                    int kb = t * skew + pos[t];
+                    if (kb >= nkb) kb -= nkb;
+                    const int nk = kb + 1 < nkb ? 2 : 1, j = kb >> 1;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC0);
+                    const uint32_t a0 = smem_u32(smem + C::A0_OFF + t * C::A0_BYTES);
+                    const uint32_t b0 = smem_u32(smem + C::W0_OFF + t * C::W0_BYTES + j * C::W0_CHUNK);
+                    const uint64_t ahi = make_desc<ROWB0>(a0), alo = make_desc<ROWB0>(a0 + C::A0_PART);
+                    const uint64_t bhi = make_desc<ROWB0>(b0), blo = make_desc<ROWB0>(b0 + C::W0_CHUNK_PART);
+#pragma unroll
+                    for (int ks = 0; ks < K0P / 8; ++ks) {
+                        const uint64_t o = (uint64_t)(ks * 2);
+                        tc_mma_tf32(d_tmem, ahi + o, bhi + o, IDESC0, ks != 0);
+                        tc_mma_tf32(d_tmem, alo + o, bhi + o, IDESC0, 1);
+                        tc_mma_tf32(d_tmem, ahi + o, blo + o, IDESC0, 1);
+                    }
+                    tc_commit(&acc0_full[t]);
+                    ++l0cnt[t];
+                    pos[t] += nk;
+                    if (pos[t] >= nkb) { pos[t] = 0; ++k[t]; fresh[t] = true; }
+                }
+            }
+        }
     } else if (warp >= 16) {
-        // ================= MMA issuers: one thread per track (a track that waits for its epilogue
+        // ================= layer-1 issuers: one thread per track (a track that waits for its epilogue
         // or its mid-stage does not hold the other one up; they drift at most NB W1 stages apart) ====
         if (lane == 0) {
             const int t = warp - 16;
-            uint32_t l0cnt = 0, w0loads = 0;
-            int curp = -1;
-            // layer-0 MMA of chunk starting at K-block kbc of tile k (first = first chunk of that tile)
-            auto issue_l0 = [&](int k, int j, bool first) {
-                if (first) {
-                    const int p = (int)((T0 + 2 * k + t) / tiles_p);
-                    if (p != curp) { mbar_wait(&w0_full[t], w0loads & 1); ++w0loads; curp = p; }
-                    mbar_wait(&a0_full[t], (uint32_t)k & 1);
-                }
-                mbar_wait(&acc0_empty[t], (l0cnt & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC0);
-                const uint32_t a0 = smem_u32(smem + C::A0_OFF + t * C::A0_BYTES);
-                const uint32_t b0 = smem_u32(smem + C::W0_OFF + t * C::W0_BYTES + j * C::W0_CHUNK);
-                const uint64_t ahi = make_desc<ROWB0>(a0), alo = make_desc<ROWB0>(a0 + C::A0_PART);
-                const uint64_t bhi = make_desc<ROWB0>(b0), blo = make_desc<ROWB0>(b0 + C::W0_CHUNK_PART);
-#pragma unroll
-                for (int ks = 0; ks < K0P / 8; ++ks) {
-                    const uint64_t o = (uint64_t)(ks * 2);
-                    tc_mma_tf32(d_tmem, ahi + o, bhi + o, IDESC0, ks != 0);
-                    tc_mma_tf32(d_tmem, alo + o, bhi + o, IDESC0, 1);
-                    tc_mma_tf32(d_tmem, ahi + o, blo + o, IDESC0, 1);
-                }
-                tc_commit(&acc0_full[t]);
-                ++l0cnt;
-            };
             uint32_t s = 0, bph = 0, slot = 0, sph = 0;
             int kb = 0, k = 0, pos = 0;
             for (int nb = 0; nb < nblk; ++nb) {
@@ -341,18 +368,6 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                 if (nb < t * skew || k >= ntl[t]) {
                     mbar_arrive(&b_empty[s]);               // this track does not use the block
                 } else {
-                    if (k == 0 && pos == 0) issue_l0(0, kb >> 1, true);
-                    if ((kb & 1) == 0) {
-                        // chunk boundary: queue the NEXT chunk's layer-0 MMA behind the mid-stage's drain
-                        const int nk = kb + 1 < nkb ? 2 : 1;
-                        if (pos + nk < nkb) {
-                            int kb2 = kb + nk;
-                            if (kb2 >= nkb) kb2 -= nkb;
-                            issue_l0(k, kb2 >> 1, false);
-                        } else if (k + 1 < ntl[t]) {
-                            issue_l0(k + 1, (t * skew) >> 1, true);
-                        }
-                    }
                     if (pos == 0) mbar_wait(&acc1_empty[t], ((uint32_t)k & 1) ^ 1);
                     mbar_wait(&a1_full[t * NS + slot], sph);
                     tc_fence_after();

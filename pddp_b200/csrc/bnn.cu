@@ -500,13 +500,12 @@ template <int GEO, bool TAN>
 static cudaError_t launch_mlp_tc2(const BnnMlpArgs<float>& a, const tc2::Images& im, cudaStream_t st) {
     typedef Geo<GEO> G;
     constexpr int K0P = G::DA + G::NU + 1 <= 8 ? 8 : 16, DP = G::D <= 4 ? 4 : 8;
-    constexpr int RPP = TAN ? G::D + 2 : 1, NPART = 4 * (32 / RPP);
     auto kern = tc2::bnn_mlp_tc2_kernel<GEO, TAN>;
     const int smem = tc2::Cfg<K0P, DP>::TOTAL + tc2::Cfg<K0P, DP>::ALIGN_PAD;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    const int S = (int)(a.total / a.net.P);                  // rows (TAN: groups of 1 + T rows) per particle
-    const int tiles_p = (S + NPART - 1) / NPART;
+    const int S = (int)(a.total / a.net.P);                  // items per particle: (problem, alpha) pairs / problems
+    const int tiles_p = (S + tc2::TILE_M - 1) / tc2::TILE_M;      // super-tiles per particle (TAN: 1 + T passes each)
     const long long ntiles = (long long)tiles_p * a.net.P;
     const int grid = (int)(ntiles < (long long)num_sms() ? ntiles : (long long)num_sms());
     kern<<<grid, tc2::THREADS, smem, st>>>(a, im, S, tiles_p, (a.net.H0 + 1 + tc2::KB - 1) / tc2::KB);

@@ -132,6 +132,24 @@ __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, float* v) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+// 16 lanes x 256 bit fragments: register 4i+{0,1} = row lane/4, columns 8i + 2*(lane%4) + {0,1};
+// register 4i+{2,3} = row lane/4 + 8, same columns (measured with tools/probe/tmem_layout.cu).
+__device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int e = 8; e < 16; ++e) r[e] = 0;
+}
 // tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled
 // above the wait.
 __device__ __forceinline__ void tc_wait_ld16(float* v) {
@@ -241,7 +259,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
     constexpr int K0P = K0 + 1 <= 8 ? 8 : 16, DP = D <= 4 ? 4 : 8;
     typedef Cfg<K0P, DP> C;
     constexpr int NB = C::NB, NS = C::NS, ROWB0 = C::ROWB0;
-    constexpr int TD = TAN ? D + G::NU : 0, RPP = 1 + TD, PPW = 32 / RPP, NPART = 4 * PPW;
+    constexpr int TD = TAN ? D + G::NU : 0, RPP = 1 + TD;     // passes per super-tile: primal + one per tangent direction
     constexpr uint32_t IDESC1 = idesc_tf32(TILE_M, TILE_N), IDESC1B = idesc_bf16(TILE_M, TILE_N), IDESC0 = idesc_tf32(TILE_M, N0);
 
     extern __shared__ unsigned char smem_raw[];
@@ -264,12 +282,16 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int P = n.P;
 
-    // ---- tile schedule: a contiguous range of (particle, row-block) tiles per CTA; track t takes
-    // every other tile of the range.  Track 1 is `skew` K-blocks behind track 0 in the W1 stream.
+    // ---- tile schedule.  A super-tile is 128 items (rollout: (problem, alpha) pairs; linearise:
+    // problems) of one particle; it is RPP consecutive MMA tiles ("passes") on one track: the primal
+    // rows, then one pass per tangent direction -- so a thread sees the primal and the tangent
+    // pre-activations of the same (item, hidden unit) and the ReLU gate never crosses lanes.
+    // Each CTA owns a contiguous range of super-tiles; track t takes every other one.  Track 1 is
+    // `skew` K-blocks behind track 0 in the W1 stream.
     const long long NT = (long long)P * tiles_p;
     const long long T0 = NT * blockIdx.x / gridDim.x, T1 = NT * (blockIdx.x + 1) / gridDim.x;
     const int cnt = (int)(T1 - T0);
-    const int ntl[2] = {(cnt + 1) / 2, cnt / 2};
+    const int ntl[2] = {((cnt + 1) / 2) * RPP, (cnt / 2) * RPP};     // MMA tiles per track
     const int skew = (nkb / 2) & ~1;
     const int nch = (nkb + 1) / 2;
     const uint32_t w0_bytes = (uint32_t)nch * C::W0_CHUNK;
@@ -323,7 +345,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                 for (int t = 0; t < 2; ++t) {
                     if (k[t] >= ntl[t]) continue;
                     if (fresh[t]) {
-                        const int p = (int)((T0 + 2 * k[t] + t) / tiles_p);
+                        const int p = (int)((T0 + 2 * (k[t] / RPP) + t) / tiles_p);
                         if (p != curp[t]) {
                             if (!mbar_test(&w0_full[t], w0loads[t] & 1)) continue;
                             ++w0loads[t];
@@ -394,63 +416,64 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
     } else {
         // ================= worker teams: warps 0-7 epilogue (track 0, 1), warps 8-15 mid-stage =================
         const int team = warp >> 2, t = team & 1;
-        const int r = tid & 127, w = r >> 5;                  // row of the tile = TMEM lane; w = lane quarter
-        const int ql = lane / RPP, d = lane - ql * RPP, q = w * PPW + ql;
-        const uint32_t primal_bit = 1u << (ql * RPP);
-        const uint32_t lane_taddr = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(t * TM_TRACK);
+        const int r = tid & 127, w = r >> 5;                  // w = TMEM lane quarter of this warp
+        const uint32_t track_taddr = tmem_base + (uint32_t)(t * TM_TRACK);
         const int nt = ntl[t];
         if (nt == 0) goto done;
         if (team >= 2) {
-            // ---------------- mid-stage: inputs -> A0, layer-0 accumulator -> A1 ----------------
-            unsigned char* A0 = smem + C::A0_OFF + t * C::A0_BYTES;
+            // ---------------- mid-stage (thread = row r): inputs -> A0, layer-0 accumulator -> A1 ----------------
+            const uint32_t A0 = smem_u32(smem + C::A0_OFF + t * C::A0_BYTES);
+            const uint32_t lane_taddr = track_taddr + ((uint32_t)(w * 32) << 16);
             const uint32_t row_off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64), row_sw = (uint32_t)((r >> 1) & 3);   // SWIZZLE_64B row
-            float xn[D], un = 0.f;
-            bool vn = false;
-            auto fetch = [&](int k) {      // row of tile k: particle p, group i -> global row i*P + p
-                const long long tau = T0 + 2 * k + t;
-                const int p = (int)(tau / tiles_p), l = (int)(tau - (long long)p * tiles_p);
-                const int i = l * NPART + q;
-                vn = ql < PPW && i < S;
+            float inc[K0], inn[K0];            // features [aug(x), u] of this row's item: current / next super-tile
+            bool vc = false, vn = false;
+            uint32_t gate[MAX_NCH];            // sign bits of the primal pre-activations, one word per chunk (TAN)
 #pragma unroll
-                for (int e = 0; e < D; ++e) xn[e] = 0.f;
-                un = 0.f;
+            for (int j = 0; j < MAX_NCH; ++j) gate[j] = 0;
+            auto fetch = [&](int ks) {         // item r of super-tile ks: particle p, item i -> global row i*P + p
+                const long long tau = T0 + 2 * ks + t;
+                const int p = (int)(tau / tiles_p), l = (int)(tau - (long long)p * tiles_p);
+                const int i = l * TILE_M + r;
+                vn = i < S;
+#pragma unroll
+                for (int k = 0; k < K0; ++k) inn[k] = 0.f;
                 if (vn) {
+                    float x[D];
                     const float* xp = a.X + ((size_t)i * P + p) * D;
                     if (D % 4 == 0) {
 #pragma unroll
-                        for (int e = 0; e < D; e += 4) *reinterpret_cast<float4*>(xn + e) = __ldg(reinterpret_cast<const float4*>(xp + e));
+                        for (int e = 0; e < D; e += 4) *reinterpret_cast<float4*>(x + e) = __ldg(reinterpret_cast<const float4*>(xp + e));
                     } else {
 #pragma unroll
-                        for (int e = 0; e < D; e += 2) *reinterpret_cast<float2*>(xn + e) = __ldg(reinterpret_cast<const float2*>(xp + e));
+                        for (int e = 0; e < D; e += 2) *reinterpret_cast<float2*>(x + e) = __ldg(reinterpret_cast<const float2*>(xp + e));
                     }
-                    un = __ldg(a.u + i);
+#pragma unroll
+                    for (int i2 = 0; i2 < NNA; ++i2) inn[i2] = x[G::nonang(i2)];
+#pragma unroll
+                    for (int i2 = 0; i2 < NANG; ++i2) { inn[NNA + 2 * i2] = sinf(x[G::ang(i2)]); inn[NNA + 2 * i2 + 1] = cosf(x[G::ang(i2)]); }
+                    inn[DA] = __ldg(a.u + i);
                 }
             };
-            auto write_a0 = [&]() {        // [norm(aug(x), u), 1] (primal) or its tangent along direction d-1
+            auto write_a0 = [&](int d) {       // [norm(aug(x), u), 1] (d == 0) or its tangent along direction d-1
                 float row[K0P];
 #pragma unroll
                 for (int k = 0; k < K0P; ++k) row[k] = 0.f;
-                if (vn) {
-                    float in[K0], sc[K0];
+                if (vc) {
+                    float sc[K0];
 #pragma unroll
                     for (int k = 0; k < K0; ++k) sc[k] = n.X_std_inv ? n.X_std_inv[k] : 1.f;
-#pragma unroll
-                    for (int i = 0; i < NNA; ++i) in[i] = xn[G::nonang(i)];
-#pragma unroll
-                    for (int i = 0; i < NANG; ++i) { in[NNA + 2 * i] = sinf(xn[G::ang(i)]); in[NNA + 2 * i + 1] = cosf(xn[G::ang(i)]); }
-                    in[DA] = un;
                     if (!TAN || d == 0) {
 #pragma unroll
-                        for (int k = 0; k < K0; ++k) row[k] = (in[k] - (n.X_mean ? n.X_mean[k] : 0.f)) * sc[k];
+                        for (int k = 0; k < K0; ++k) row[k] = (inc[k] - (n.X_mean ? n.X_mean[k] : 0.f)) * sc[k];
                         row[K0] = 1.f;
                     } else {
                         const int dir = d - 1;
 #pragma unroll
-                        for (int i = 0; i < NNA; ++i) if (dir == G::nonang(i)) row[i] = sc[i];
+                        for (int i2 = 0; i2 < NNA; ++i2) if (dir == G::nonang(i2)) row[i2] = sc[i2];
 #pragma unroll
-                        for (int i = 0; i < NANG; ++i) if (dir == G::ang(i)) {
-                            row[NNA + 2 * i] = in[NNA + 2 * i + 1] * sc[NNA + 2 * i];
-                            row[NNA + 2 * i + 1] = -in[NNA + 2 * i] * sc[NNA + 2 * i + 1];
+                        for (int i2 = 0; i2 < NANG; ++i2) if (dir == G::ang(i2)) {
+                            row[NNA + 2 * i2] = inc[NNA + 2 * i2 + 1] * sc[NNA + 2 * i2];          // d sin = cos
+                            row[NNA + 2 * i2 + 1] = -inc[NNA + 2 * i2] * sc[NNA + 2 * i2 + 1];     // d cos = -sin
                         }
                         if (dir == D) row[DA] = sc[DA];
                     }
@@ -461,8 +484,8 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
 #pragma unroll
                     for (int e = 0; e < 4; ++e) split_tf32(row[4 * c + e], hi[e], lo[e]);
                     const uint32_t off = swz<ROWB0>(r, 4 * c);
-                    sts128f(smem_u32(A0) + off, hi[0], hi[1], hi[2], hi[3]);
-                    sts128f(smem_u32(A0) + C::A0_PART + off, lo[0], lo[1], lo[2], lo[3]);
+                    sts128f(A0 + off, hi[0], hi[1], hi[2], hi[3]);
+                    sts128f(A0 + C::A0_PART + off, lo[0], lo[1], lo[2], lo[3]);
                 }
                 fence_async_smem();
                 mbar_arrive(&a0_full[t]);
@@ -474,15 +497,20 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
             int curp = (int)((T0 + t) / tiles_p);
             if (r == 0) load_w0(curp);
             fetch(0);
-            write_a0();
+#pragma unroll
+            for (int k = 0; k < K0; ++k) inc[k] = inn[k];
+            vc = vn;
+            write_a0(0);
             uint32_t ci = 0, slot = 0, sph = 1;
             const int kb0 = t * skew;
+            int ks = 0, d = 0;                 // super-tile and pass of the current tile
             for (int k = 0; k < nt; ++k) {
-                if (k + 1 < nt) fetch(k + 1);
+                const bool last_pass = d == RPP - 1;
+                if (last_pass && k + 1 < nt) fetch(ks + 1);
                 for (int pos = 0; pos < nkb;) {
                     int kb = kb0 + pos;
                     if (kb >= nkb) kb -= nkb;
-                    const int nk = kb + 1 < nkb ? 2 : 1;
+                    const int nk = kb + 1 < nkb ? 2 : 1, j = kb >> 1;
                     float v[32];
                     mbar_wait(&acc0_full[t], ci & 1);
                     ++ci;
@@ -492,20 +520,36 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                     tc_fence_before();
                     mbar_arrive(&acc0_empty[t]);
                     if (pos + nk >= nkb && k + 1 < nt) {
-                        // every layer-0 MMA of this tile has completed: A0 and the W0 image are free
-                        const int pn = (int)((T0 + 2 * (k + 1) + t) / tiles_p);
-                        if (pn != curp) { if (r == 0) load_w0(pn); curp = pn; }
-                        write_a0();
-                    }
-                    if (TAN) {
+                        // every layer-0 MMA of this tile has completed: A0 (and, between super-tiles, the W0 image) is free
+                        if (last_pass) {
+                            const int pn = (int)((T0 + 2 * (ks + 1) + t) / tiles_p);
+                            if (pn != curp) { if (r == 0) load_w0(pn); curp = pn; }
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const unsigned on = __ballot_sync(0xffffffffu, v[e] > 0.f);
-                            v[e] = (on & primal_bit) ? v[e] : 0.f;
+                            for (int k2 = 0; k2 < K0; ++k2) inc[k2] = inn[k2];
+                            vc = vn;
+                            write_a0(0);
+                        } else {
+                            write_a0(d + 1);
                         }
-                    } else {
+                    }
+                    if (!TAN) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+                    } else if (d == 0) {
+                        uint32_t word = 0;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            word = __funnelshift_l(__float_as_uint(v[e]), word, 1);     // sign of v[e] ends up at bit 31 - e
+                            v[e] = fmaxf(v[e], 0.f);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < MAX_NCH; ++jj) if (jj == j) gate[jj] = word;
+                    } else {
+                        uint32_t word = 0;
+#pragma unroll
+                        for (int jj = 0; jj < MAX_NCH; ++jj) if (jj == j) word = gate[jj];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = (word & (0x80000000u >> e)) ? 0.f : v[e];
                     }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -537,18 +581,26 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                     }
                     pos += nk;
                 }
+                if (++d == RPP) { d = 0; ++ks; }
             }
         } else {
             // ---------------- epilogue: layer-1 accumulator -> ReLU -> output layer -> X', dX'/d(X,u) ----------------
+            // 16x256b TMEM fragments: this thread holds rows 32w + 16hf + 8hb + lane/4 (hf, hb in {0,1}) and, of
+            // every group of 8 columns, columns 2*(lane%4) and +1 -- so one pair of LDS.128 of the output weights
+            // feeds 4 rows (a thread-per-row layout needs a broadcast LDS.128 per column: 4x the shared-memory
+            // wavefronts, and this kernel is bound by the shared-memory pipe).  Column sums are completed
+            // across the 4 lanes of a quad with two shuffles per value.
             const uint32_t W2s = smem_u32(smem + C::W2_OFF + t * C::W2_BYTES);
+            const int q4 = lane & 3, rq = lane >> 2;
             int curp = -1;
             uint32_t w2loads = 0;
+            uint32_t gate[7];                  // sign bits of this thread's 208 primal pre-activations (TAN)
+#pragma unroll
+            for (int j = 0; j < 7; ++j) gate[j] = 0;
+            int ks = 0, d = 0;
             for (int k = 0; k < nt; ++k) {
-                const long long tau = T0 + 2 * k + t;
+                const long long tau = T0 + 2 * ks + t;
                 const int p = (int)(tau / tiles_p), l = (int)(tau - (long long)p * tiles_p);
-                const int i = l * NPART + q;
-                const bool valid = ql < PPW && i < S;
-                const size_t g = (size_t)i * P + p;
                 if (p != curp) {
                     named_bar_sync(1 + t, 128);      // every warp of the team is done with the old weights
                     if (r == 0) {
@@ -559,59 +611,91 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
                     ++w2loads;
                     curp = p;
                 }
-                float x0[D];
+                float y[4][D];
 #pragma unroll
-                for (int o = 0; o < D; ++o) x0[o] = 0.f;
-                if (valid && (!TAN || d == 0)) {
+                for (int jr = 0; jr < 4; ++jr)
 #pragma unroll
-                    for (int o = 0; o < D; ++o) x0[o] = __ldg(a.X + g * D + o);
-                }
-                float y[D];
-#pragma unroll
-                for (int o = 0; o < D; ++o) y[o] = 0.f;
+                    for (int o = 0; o < D; ++o) y[jr][o] = 0.f;
                 mbar_wait(&acc1_full[t], (uint32_t)k & 1);
                 tc_fence_after();
-                // the accumulator is drained in batches of 64 columns: one TMEM round trip per batch
 #pragma unroll
-                for (int c0 = 0; c0 < TILE_N; c0 += 64) {
-                    constexpr int NQ_MAX = 4;
-                    float buf[16 * NQ_MAX];
-                    const int nq = (TILE_N - c0) / 16 < NQ_MAX ? (TILE_N - c0) / 16 : NQ_MAX;
+                for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+                    constexpr int NG_MAX = 4;                                   // 8-column groups per batch
+                    const int ng = (TILE_N - c0) / 8 < NG_MAX ? (TILE_N - c0) / 8 : NG_MAX;
+                    float f[2][4 * NG_MAX];
 #pragma unroll
-                    for (int qd = 0; qd < NQ_MAX; ++qd)
-                        if (qd < nq) tc_ld16_nowait(lane_taddr + TM_ACC1 + c0 + 16 * qd, buf + 16 * qd);
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const uint32_t ta = track_taddr + ((uint32_t)(w * 32 + hf * 16) << 16) + TM_ACC1 + c0;
+                        if (ng == 4) tc_ld_16x256b_x4(ta, f[hf]);
+                        else tc_ld_16x256b_x2(ta, f[hf]);
+                    }
+                    tc_wait_ld16(f[0]);
+                    tc_wait_ld16(f[1]);
 #pragma unroll
-                    for (int qd = 0; qd < NQ_MAX; ++qd)
-                        if (qd < nq) tc_wait_ld16(buf + 16 * qd);
+                    for (int gi = 0; gi < NG_MAX; ++gi) {
+                        if (gi < ng) {
+                            float w2[2][DP];                                    // output weights of this thread's 2 columns
 #pragma unroll
-                    for (int e = 0; e < 16 * NQ_MAX; ++e) {
-                        if (e < 16 * nq) {
-                            float vv;
-                            if (TAN) {
-                                const unsigned on = __ballot_sync(0xffffffffu, buf[e] > 0.f);
-                                vv = (on & primal_bit) ? buf[e] : 0.f;
-                            } else {
-                                vv = fmaxf(buf[e], 0.f);
-                            }
-                            float w2[DP];
+                            for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
-                            for (int o4 = 0; o4 < DP / 4; ++o4)
-                                *reinterpret_cast<float4*>(w2 + 4 * o4) = lds128f(W2s + (uint32_t)(((c0 + e) * DP + 4 * o4) * 4));
+                                for (int o4 = 0; o4 < DP / 4; ++o4)
+                                    *reinterpret_cast<float4*>(&w2[cc][4 * o4]) =
+                                        lds128f(W2s + (uint32_t)(((c0 + 8 * gi + 2 * q4 + cc) * DP + 4 * o4) * 4));
 #pragma unroll
-                            for (int o = 0; o < D; ++o) y[o] += vv * w2[o];
+                            for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                                for (int hb = 0; hb < 2; ++hb)
+#pragma unroll
+                                    for (int cc = 0; cc < 2; ++cc) {
+                                        float vv = f[hf][4 * gi + 2 * hb + cc];
+                                        // element index of this value inside the thread's 208: fixed at compile time
+                                        const int eidx = ((c0 / 8 + gi) * 2 + hf) * 4 + 2 * hb + cc;
+                                        if (!TAN) {
+                                            vv = fmaxf(vv, 0.f);
+                                        } else if (d == 0) {
+                                            gate[eidx >> 5] = __funnelshift_l(__float_as_uint(vv), gate[eidx >> 5], 1);
+                                            vv = fmaxf(vv, 0.f);
+                                        } else {
+                                            // the sign was shifted in at position eidx%32 of its word: it sits at bit (n_w - 1 - eidx%32)
+                                            const int nw = (eidx >> 5) < 6 ? 32 : 16;
+                                            vv = (gate[eidx >> 5] & (1u << (nw - 1 - (eidx & 31)))) ? 0.f : vv;
+                                        }
+#pragma unroll
+                                        for (int o = 0; o < D; ++o) y[2 * hf + hb][o] += vv * w2[cc][o];
+                                    }
                         }
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(&acc1_empty[t]);
-                if (valid) {
+                // complete the column sums across the quad, then lane q4 writes outputs o = q4 (and q4 + 4)
+#pragma unroll
+                for (int jr = 0; jr < 4; ++jr)
 #pragma unroll
                     for (int o = 0; o < D; ++o) {
-                        const float sd = n.dX_std ? n.dX_std[o] : 1.f, mn = n.dX_mean ? n.dX_mean[o] : 0.f;
-                        if (!TAN || d == 0) a.Xn[g * D + o] = x0[o] + ((y[o] + n.b2[o]) * sd + mn);
-                        else a.Jp[(g * D + o) * TD + (d - 1)] = ((d - 1) == o ? 1.f : 0.f) + y[o] * sd;
+                        y[jr][o] += __shfl_xor_sync(0xffffffffu, y[jr][o], 1);
+                        y[jr][o] += __shfl_xor_sync(0xffffffffu, y[jr][o], 2);
+                    }
+#pragma unroll
+                for (int oo = 0; oo < (D + 3) / 4; ++oo) {
+                    const int o = q4 + 4 * oo;
+                    if (o < D) {
+                        const float sd = n.dX_std ? n.dX_std[o] : 1.f, mn = n.dX_mean ? n.dX_mean[o] : 0.f, bo = n.b2[o];
+#pragma unroll
+                        for (int jr = 0; jr < 4; ++jr) {
+                            const int i = l * TILE_M + w * 32 + (jr >> 1) * 16 + (jr & 1) * 8 + rq;
+                            if (i < S) {
+                                float yo = 0.f;
+#pragma unroll
+                                for (int o2 = 0; o2 < D; ++o2) if (o2 == o) yo = y[jr][o2];
+                                const size_t g = (size_t)i * P + p;
+                                if (!TAN || d == 0) a.Xn[g * D + o] = __ldg(a.X + g * D + o) + ((yo + bo) * sd + mn);
+                                else a.Jp[(g * D + o) * TD + (d - 1)] = ((d - 1) == o ? 1.f : 0.f) + yo * sd;
+                            }
+                        }
                     }
                 }
+                if (++d == RPP) { d = 0; ++ks; }
             }
         }
     }

@@ -51,6 +51,11 @@ __device__ __forceinline__ int boxqp1(T x0, T Q, T c, T lo, T hi, T& x, bool& is
         while ((fc - old_f) / (step * sdotg) < armijo) {
             step *= step_dec;
             xc = clampv(x + step * search, lo, hi);
+            // Once the candidate rounds back onto x it stays there for every smaller step: the
+            // reference keeps shrinking the step ~110 times down to min_step and then leaves x
+            // unchanged with result 2 ("no descent direction").  Same outcome, without the spin --
+            // at the optimum the search direction is rounding noise, so this is the COMMON case.
+            if (xc == x) { fc = old_f; result = 2; break; }
             fc = T(0.5) * xc * Q * xc + xc * c;
             if (step < min_step) { result = 2; break; }
         }
@@ -81,8 +86,35 @@ __device__ __forceinline__ bool gains1(T Quu, T Qu, T reg, bool bounded, T lo, T
 }
 
 // ------------------------------------------------------------------------------------------
+// One time step's inputs of one problem, held in registers.  The time loop is a dependent chain
+// (V_z, V_zz), but its INPUTS are not: the record of step t-DEPTH is requested before step t is
+// computed, so every thread always has DEPTH records (17 floats at nz = 2) in flight -- that, times
+// the resident threads, is what keeps HBM busy in a thread-per-problem scan.
 template <class T, int NZ>
-__global__ void __launch_bounds__(128) backward_thread_kernel(const BackwardArgs<T> a) {
+struct BackwardRec {
+    T Fz[NZ][NZ], Fu[NZ], Lz[NZ], Luz[NZ], Lzz[NZ][NZ], Lu, Luu, U;
+};
+template <class T, int NZ>
+__device__ __forceinline__ void backward_load(const BackwardArgs<T>& a, int b, int t, bool bounded, BackwardRec<T, NZ>& r) {
+#pragma unroll
+    for (int i = 0; i < NZ; ++i) {
+        r.Fu[i] = __ldg(a.F_u + a.lFu.at(b, t, i));
+        r.Lz[i] = __ldg(a.L_z + a.lLz.at(b, t, i));
+        r.Luz[i] = __ldg(a.L_uz + a.lLuz.at(b, t, i));
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) {
+            r.Fz[i][j] = __ldg(a.F_z + a.lFz.at(b, t, i * NZ + j));
+            r.Lzz[i][j] = __ldg(a.L_zz + a.lLzz.at(b, t, i * NZ + j));
+        }
+    }
+    r.Lu = __ldg(a.L_u + a.lLu.at(b, t, 0));
+    r.Luu = __ldg(a.L_uu + a.lLuu.at(b, t, 0));
+    r.U = bounded ? __ldg(a.U + a.lU.at(b, t, 0)) : T(0);
+}
+
+template <class T, int NZ>
+__global__ void __launch_bounds__(128, (sizeof(T) == 4 && NZ <= 2) ? 5 : 2) backward_thread_kernel(const BackwardArgs<T> a) {
+    constexpr bool DEEP = NZ <= 2;          // two records in flight where they fit in registers
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
     if (a.active && a.active[b] == 0) return;
@@ -90,6 +122,9 @@ __global__ void __launch_bounds__(128) backward_thread_kernel(const BackwardArgs
     const T reg = (T)a.mu[b];
     T lo = T(0), hi = T(0);
     if (bounded) { lo = a.u_min[0]; hi = a.u_max[0]; }
+    BackwardRec<T, NZ> c, nx1, nx2;
+    backward_load<T, NZ>(a, b, a.N - 1, bounded, c);
+    if (DEEP && a.N >= 2) backward_load<T, NZ>(a, b, a.N - 2, bounded, nx1);
     T v[NZ], V[NZ][NZ];
 #pragma unroll
     for (int i = 0; i < NZ; ++i) {
@@ -99,76 +134,75 @@ __global__ void __launch_bounds__(128) backward_thread_kernel(const BackwardArgs
     }
     T k_next = T(0);
     bool ok = true;
+#pragma unroll 1
     for (int t = a.N - 1; t >= 0; --t) {
-        T Fz[NZ][NZ], Fu[NZ];
+        {
+            if (DEEP) { if (t >= 2) backward_load<T, NZ>(a, b, t - 2, bounded, nx2); }
+            else if (t >= 1) backward_load<T, NZ>(a, b, t - 1, bounded, nx1);
+            T W[NZ][NZ], wu[NZ];                               // W = V Fz, wu = V Fu
 #pragma unroll
-        for (int i = 0; i < NZ; ++i) {
-            Fu[i] = a.F_u[a.lFu.at(b, t, i)];
+            for (int i = 0; i < NZ; ++i) {
+                T su = T(0);
 #pragma unroll
-            for (int j = 0; j < NZ; ++j) Fz[i][j] = a.F_z[a.lFz.at(b, t, i * NZ + j)];
-        }
-        T W[NZ][NZ], wu[NZ];                               // W = V Fz, wu = V Fu
+                for (int kk = 0; kk < NZ; ++kk) su += V[i][kk] * c.Fu[kk];
+                wu[i] = su;
 #pragma unroll
-        for (int i = 0; i < NZ; ++i) {
-            T su = T(0);
+                for (int j = 0; j < NZ; ++j) {
+                    T sacc = T(0);
 #pragma unroll
-            for (int kk = 0; kk < NZ; ++kk) su += V[i][kk] * Fu[kk];
-            wu[i] = su;
-#pragma unroll
-            for (int j = 0; j < NZ; ++j) {
-                T s = T(0);
-#pragma unroll
-                for (int kk = 0; kk < NZ; ++kk) s += V[i][kk] * Fz[kk][j];
-                W[i][j] = s;
+                    for (int kk = 0; kk < NZ; ++kk) sacc += V[i][kk] * c.Fz[kk][j];
+                    W[i][j] = sacc;
+                }
             }
-        }
-        T Qz[NZ], Quz[NZ], Qzz[NZ][NZ];
-        T Qu = a.L_u[a.lLu.at(b, t, 0)], Quu = a.L_uu[a.lLuu.at(b, t, 0)];
-#pragma unroll
-        for (int kk = 0; kk < NZ; ++kk) {
-            Qu += Fu[kk] * v[kk];
-            Quu += Fu[kk] * wu[kk];
-        }
-#pragma unroll
-        for (int i = 0; i < NZ; ++i) {
-            T sz = a.L_z[a.lLz.at(b, t, i)], suz = a.L_uz[a.lLuz.at(b, t, i)];
+            T Qz[NZ], Quz[NZ], Qzz[NZ][NZ];
+            T Qu = c.Lu, Quu = c.Luu;
 #pragma unroll
             for (int kk = 0; kk < NZ; ++kk) {
-                sz += Fz[kk][i] * v[kk];
-                suz += Fu[kk] * W[kk][i];
+                Qu += c.Fu[kk] * v[kk];
+                Quu += c.Fu[kk] * wu[kk];
             }
-            Qz[i] = sz;
-            Quz[i] = suz;
 #pragma unroll
-            for (int j = 0; j < NZ; ++j) {
-                T s = a.L_zz[a.lLzz.at(b, t, i * NZ + j)];
+            for (int i = 0; i < NZ; ++i) {
+                T sz = c.Lz[i], suz = c.Luz[i];
 #pragma unroll
-                for (int kk = 0; kk < NZ; ++kk) s += Fz[kk][i] * W[kk][j];
-                Qzz[i][j] = s;
+                for (int kk = 0; kk < NZ; ++kk) {
+                    sz += c.Fz[kk][i] * v[kk];
+                    suz += c.Fu[kk] * W[kk][i];
+                }
+                Qz[i] = sz;
+                Quz[i] = suz;
+#pragma unroll
+                for (int j = 0; j < NZ; ++j) {
+                    T sacc = c.Lzz[i][j];
+#pragma unroll
+                    for (int kk = 0; kk < NZ; ++kk) sacc += c.Fz[kk][i] * W[kk][j];
+                    Qzz[i][j] = sacc;
+                }
             }
+            T kt, inv;
+            ok = gains1(Quu, Qu, reg, bounded, lo - c.U, hi - c.U, k_next, kt, inv);
+            T Kt[NZ];
+#pragma unroll
+            for (int i = 0; i < NZ; ++i) {
+                Kt[i] = -Quz[i] * inv;
+                if (Kt[i] != Kt[i]) ok = false;
+            }
+            if (!ok) break;
+            k_next = kt;
+            a.k[a.lk.at(b, t, 0)] = kt;
+#pragma unroll
+            for (int i = 0; i < NZ; ++i) a.K[a.lK.at(b, t, i)] = Kt[i];
+            // value update with the UN-regularised Q_uu (ref: ilqr.py:664-672)
+#pragma unroll
+            for (int i = 0; i < NZ; ++i) v[i] = Qz[i] + Kt[i] * Qu + Kt[i] * Quu * kt + Quz[i] * kt;
+#pragma unroll
+            for (int i = 0; i < NZ; ++i)
+#pragma unroll
+                for (int j = 0; j < NZ; ++j)
+                    V[i][j] = T(0.5) * (Qzz[i][j] + Qzz[j][i]) + Kt[i] * Quu * Kt[j] + Kt[i] * Quz[j] + Quz[i] * Kt[j];
         }
-        T kt, inv;
-        T ut = bounded ? a.U[a.lU.at(b, t, 0)] : T(0);
-        ok = gains1(Quu, Qu, reg, bounded, lo - ut, hi - ut, k_next, kt, inv);
-        T Kt[NZ];
-#pragma unroll
-        for (int i = 0; i < NZ; ++i) {
-            Kt[i] = -Quz[i] * inv;
-            if (Kt[i] != Kt[i]) ok = false;
-        }
-        if (!ok) break;
-        k_next = kt;
-        a.k[a.lk.at(b, t, 0)] = kt;
-#pragma unroll
-        for (int i = 0; i < NZ; ++i) a.K[a.lK.at(b, t, i)] = Kt[i];
-        // value update with the UN-regularised Q_uu (ref: ilqr.py:664-672)
-#pragma unroll
-        for (int i = 0; i < NZ; ++i) v[i] = Qz[i] + Kt[i] * Qu + Kt[i] * Quu * kt + Quz[i] * kt;
-#pragma unroll
-        for (int i = 0; i < NZ; ++i)
-#pragma unroll
-            for (int j = 0; j < NZ; ++j)
-                V[i][j] = T(0.5) * (Qzz[i][j] + Qzz[j][i]) + Kt[i] * Quu * Kt[j] + Kt[i] * Quz[j] + Quz[i] * Kt[j];
+        c = nx1;
+        if (DEEP) nx1 = nx2;
     }
     a.status[b] = ok ? 0 : 1;
 }

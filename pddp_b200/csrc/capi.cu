@@ -157,7 +157,7 @@ static int rollout_known_t(const pddp_shape* s, const pddp_known_dynamics* dyn, 
     const int64_t B = s->B, N = s->N, nz = s->nz, nu = s->nu, ly = s->layout;
     a.lZ = make_layout(ly, B, N + 1, nz); a.lU = make_layout(ly, B, N, nu);
     a.lk = make_layout(ly, B, N, nu); a.lK = make_layout(ly, B, N, nu * nz);
-    note_launches(1);
+    note_launches(2);
     return cuda_result(rollout_known<T>(s->geo, s->enc, a, st), "pddp_rollout_known");
 }
 

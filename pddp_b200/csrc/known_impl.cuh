@@ -226,7 +226,20 @@ __global__ void __launch_bounds__(128) rollout_known_kernel(const RollKnownArgs<
         a.amin[b] = idx;
         a.J_new[b] = best;
     }
-    if (lane == idx) roll_one<T, GEO, ENC, true>(a, b, alpha, bounded, lo, hi);
+}
+
+// Second pass: ONE THREAD PER PROBLEM re-rolls the winning alpha and stores its trajectory.  Done
+// inside the kernel above, only one lane of each alpha group would be busy: the same warp-level
+// instruction count as the all-alpha pass for 1/16 of the useful work.  Here every lane works, and
+// with the BATCH_INNER layout every store is a coalesced line.
+template <class T, int GEO, int ENC>
+__global__ void __launch_bounds__(128) rollout_known_store_kernel(const RollKnownArgs<T> a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    if ((a.active && a.active[b] == 0) || (a.bw_status && a.bw_status[b] != 0)) return;
+    const bool bounded = a.u_min != nullptr && a.u_max != nullptr;
+    const T lo = bounded ? a.u_min[0] : T(0), hi = bounded ? a.u_max[0] : T(0);
+    roll_one<T, GEO, ENC, true>(a, b, a.alphas[a.amin[b]], bounded, lo, hi);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -248,6 +261,7 @@ static cudaError_t launch_roll(const RollKnownArgs<T>& a, cudaStream_t s) {
         int64_t total = (int64_t)a.B * 32;
         rollout_known_kernel<T, GEO, ENC, 32><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(a);
     }
+    rollout_known_store_kernel<T, GEO, ENC><<<(a.B + threads - 1) / threads, threads, 0, s>>>(a);
     return cudaGetLastError();
 }
 

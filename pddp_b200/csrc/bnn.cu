@@ -268,12 +268,15 @@ struct RollStepArgs {
     Layout lZ, lU, lk, lK;
 };
 
+// One THREAD per (problem, alpha): a warp-per-pair version left 31 lanes idle through the control
+// law and the cost (the moment-matched cost of an uncertain state is the long part) and spent most
+// of its issue slots on shuffles.  The 2 x P x D particle reads per thread are contiguous and L2
+// resident (the MLP kernel has just written them).
 template <class T, int GEO, int ENC>
-__global__ void __launch_bounds__(128) bnn_roll_step_kernel(const RollStepArgs<T> a) {
+__global__ void __launch_bounds__(64) bnn_roll_step_kernel(const RollStepArgs<T> a) {
     typedef Geo<GEO> G;
-    constexpr int D = G::D, NZ = enc_size(D, ENC), NT = D * (D + 1) / 2;
-    const int lane = threadIdx.x & 31;
-    const long long s = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    constexpr int D = G::D, NZ = enc_size(D, ENC);
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (s >= (long long)a.B * a.A) return;
     const int b = (int)(s / a.A), al = (int)(s - (long long)b * a.A);
     if ((a.active && a.active[b] == 0) || (a.bw_status && a.bw_status[b] != 0)) return;
@@ -284,44 +287,44 @@ __global__ void __launch_bounds__(128) bnn_roll_step_kernel(const RollStepArgs<T
 #pragma unroll
         for (int e = 0; e < NZ; ++e) zn[e] = a.Z[a.lZ.at(b, 0, e)];
     } else {
-        T msum[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) msum[d] = T(0);
-        for (int p = lane; p < P; p += 32)
-#pragma unroll
-            for (int d = 0; d < D; ++d) msum[d] += a.Xn[((size_t)s * P + p) * D + d];
+        const T* X = a.Xn + (size_t)s * P * D;
         T M[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) M[d] = warp_sum(msum[d]) / T(P);
-        T csum[NT];
+        for (int d = 0; d < D; ++d) M[d] = T(0);
+#pragma unroll 5
+        for (int p = 0; p < P; ++p)
 #pragma unroll
-        for (int i = 0; i < NT; ++i) csum[i] = T(0);
-        for (int p = lane; p < P; p += 32) {
-            T xc[D];
+            for (int d = 0; d < D; ++d) M[d] += X[p * D + d];
 #pragma unroll
-            for (int d = 0; d < D; ++d) xc[d] = a.Xn[((size_t)s * P + p) * D + d] - M[d];
-#pragma unroll
-            for (int r = 0; r < D; ++r)
-#pragma unroll
-                for (int c = r; c < D; ++c) csum[tri<D>(r, c)] += xc[r] * xc[c];
-        }
+        for (int d = 0; d < D; ++d) M[d] /= T(P);
         T Cov[D][D], Un[D][D];
 #pragma unroll
         for (int r = 0; r < D; ++r)
 #pragma unroll
+            for (int c = 0; c < D; ++c) Cov[r][c] = T(0);
+#pragma unroll 5
+        for (int p = 0; p < P; ++p) {
+            T xc[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) xc[d] = X[p * D + d] - M[d];
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+                for (int c = r; c < D; ++c) Cov[r][c] += xc[r] * xc[c];
+        }
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
             for (int c = r; c < D; ++c) {
-                T v = warp_sum(csum[tri<D>(r, c)]) / T(P - 1);
-                Cov[r][c] = v;
-                Cov[c][r] = v;
+                Cov[r][c] /= T(P - 1);
+                Cov[c][r] = Cov[r][c];
             }
         ok = encode_moments<D, ENC, T>(M, Cov, zn, Un);
     }
     T* zrow = a.Zall + ((size_t)s * (a.N + 1) + t1) * NZ;
 #pragma unroll
-    for (int e = 0; e < NZ; ++e)
-        if ((e & 31) == lane) zrow[e] = zn[e];
-    if (lane != 0) return;
-    if (!ok && a.status) a.status[b] |= 2;
+    for (int e = 0; e < NZ; ++e) zrow[e] = zn[e];
+    if (!ok && a.status) atomicOr(&a.status[b], 2);
     T J = a.t < 0 ? T(0) : a.J[s];
     if (t1 < a.N) {                                       // control law (ref: ilqr.py:701-719)
         T du = a.alphas[al] * a.k[a.lk.at(b, t1, 0)];
@@ -636,9 +639,9 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     r.lk = make_layout(ly, B, N, nu); r.lK = make_layout(ly, B, N, nu * nz);
     bnn_init_particles_kernel<T, GEO, ENC><<<(unsigned)((total + 127) / 128), 128, 0, c.st>>>(
         r.Z, r.lZ, A, S, P, net.eps0, w.Xa, c.status);
-    const unsigned rgrid = (unsigned)((S * 32 + 127) / 128);
+    const unsigned rgrid = (unsigned)((S + 63) / 64);
     r.t = -1; r.Xn = w.Xa;
-    bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 128, 0, c.st>>>(r);
+    bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 64, 0, c.st>>>(r);
     CK(cudaGetLastError());
     BnnMlpArgs<T> a;
     a.net = net; a.u = w.ucur; a.Jp = nullptr; a.total = total;
@@ -650,7 +653,7 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
         prof_end(PROF_MLP_ROLL, c.st);
         r.t = t; r.Xn = nxt;
         prof_begin(PROF_ROLL_STEP, c.st);
-        bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 128, 0, c.st>>>(r);
+        bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 64, 0, c.st>>>(r);
         prof_end(PROF_ROLL_STEP, c.st);
         T* tmp = cur; cur = nxt; nxt = tmp;
     }

@@ -15,7 +15,6 @@
 #include "bnn_common.cuh"
 #include "bnn_mlp_simt.cuh"
 #include "bnn_mlp_tc.cuh"
-#include "bnn_mlp_tc2.cuh"
 #include "kernels.h"
 #include "profile.h"
 #include <stdio.h>
@@ -384,8 +383,7 @@ static int num_sms() {
 template <class T>
 struct Workspace {
     T *W0T, *W1T, *W2T, *m0T, *m1T, *Xa, *Xb, *Jp, *ucur, *J, *Zall, *Uall;
-    float* Bimg;   // tcgen05 path (v1): pre-swizzled hi/lo TF32 images of W1, [kb][hi|lo][208 x 128 B]
-    tc2::Images im;   // tcgen05 path (v2): W1 image, per-particle layer-0 images and output weights
+    tc::Images im;   // tcgen05 path: W1 image, per-particle layer-0 images and output weights
     size_t bytes;
 };
 
@@ -409,10 +407,9 @@ static Workspace<T> carve(void* base, const pddp_shape* s, const pddp_bnn* n, in
     w.J = take(S);
     w.Zall = take(S * (s->N + 1) * s->nz);
     w.Uall = take(S * s->N);
-    w.Bimg = reinterpret_cast<float*>(take((size_t)tc::MAX_KB * tc::B_STAGE_BYTES / sizeof(T)));
-    w.im.W1img = reinterpret_cast<unsigned char*>(take((size_t)tc2::MAX_NKB * tc2::B_STAGE / sizeof(T)));
-    w.im.W0img = reinterpret_cast<unsigned char*>(take(P * (size_t)tc2::Cfg<16, 8>::W0_BYTES / sizeof(T)));
-    w.im.W2p = reinterpret_cast<float*>(take(P * (size_t)tc2::TILE_N * 8 * sizeof(float) / sizeof(T)));
+    w.im.W1img = reinterpret_cast<unsigned char*>(take((size_t)tc::MAX_NKB * tc::B_STAGE / sizeof(T)));
+    w.im.W0img = reinterpret_cast<unsigned char*>(take(P * (size_t)tc::Cfg<16, 8>::W0_BYTES / sizeof(T)));
+    w.im.W2p = reinterpret_cast<float*>(take(P * (size_t)tc::TILE_N * 8 * sizeof(float) / sizeof(T)));
     w.bytes = off;
     return w;
 }
@@ -429,20 +426,14 @@ static BnnNet<T> make_net(const pddp_bnn* n, const Workspace<T>& w) {
     return r;
 }
 
-// The tcgen05 kernel covers fp32 with hidden widths in (64, 208] x (64, 224]; everything else
-// (fp64, small nets) runs the SIMT kernel.  PDDP_FORCE_SIMT=1 disables it (A/B comparisons).
+// The tcgen05 kernel covers fp32 with hidden widths in (64, 207] x (64, 208] (H0 + 1 <= 208: the
+// bias column); everything else (fp64, small nets) runs the SIMT kernel.  PDDP_FORCE_SIMT=1
+// disables it (A/B comparisons, tools/tc_stats.py).
 template <class T> static bool use_tensor_cores(int H0, int H1) { return false; }
 template <> bool use_tensor_cores<float>(int H0, int H1) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("PDDP_FORCE_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
-    return !forced && H0 > 64 && H0 <= tc::MAX_KB * tc::KBLK && H1 > 64 && H1 <= tc::TILE_N && H0 % 4 == 0 && H1 % 4 == 0;
-}
-// PDDP_MLP_V1=1 keeps the first tcgen05 kernel (bnn_mlp_tc.cuh) for A/B runs; the default is the
-// two-track kernel of bnn_mlp_tc2.cuh (needs H0 + 1 <= 208 for the bias column).
-static bool use_tc_v2(int H0, int H1) {
-    static int v1 = -1;
-    if (v1 < 0) { const char* e = getenv("PDDP_MLP_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
-    return !v1 && H0 + 1 <= tc2::MAX_NKB * tc2::KB && H1 <= tc2::TILE_N;
+    return !forced && H0 > 64 && H1 > 64 && H0 + 1 <= tc::MAX_NKB * tc::KB && H1 <= tc::TILE_N;
 }
 
 template <class T>
@@ -455,21 +446,17 @@ static cudaError_t prep_weights(const pddp_shape* s, const pddp_bnn* n, const Wo
     bnn_transpose_kernel<T><<<16, 256, 0, st>>>((const T*)n->mask0, n->P, n->H0, n->P, w.m0T);
     bnn_transpose_kernel<T><<<16, 256, 0, st>>>((const T*)n->mask1, n->P, n->H1, n->P, w.m1T);
     if (use_tensor_cores<T>(n->H0, n->H1)) {
-        if (use_tc_v2(n->H0, n->H1)) {
-            const int nkb = (n->H0 + 1 + tc2::KB - 1) / tc2::KB;
-            tc2::prep_w1_kernel<<<64, 256, 0, st>>>((const float*)n->W1, (const float*)n->b1, n->H0, n->H1, nkb,
-                                                    const_cast<unsigned char*>(w.im.W1img));
-            if (DA + 2 <= 8)
-                tc2::prep_w0_kernel<8><<<64, 256, 0, st>>>((const float*)n->W0, (const float*)n->b0, (const float*)n->mask0,
-                                                           n->P, n->H0, DA + 1, const_cast<unsigned char*>(w.im.W0img));
-            else
-                tc2::prep_w0_kernel<16><<<64, 256, 0, st>>>((const float*)n->W0, (const float*)n->b0, (const float*)n->mask0,
-                                                            n->P, n->H0, DA + 1, const_cast<unsigned char*>(w.im.W0img));
-            tc2::prep_w2_kernel<<<64, 256, 0, st>>>((const float*)n->W2, (const float*)n->mask1, n->P, n->H1, D, D <= 4 ? 4 : 8,
-                                                    const_cast<float*>(w.im.W2p));
-        } else {
-            tc::bnn_tc_prep_kernel<<<64, 256, 0, st>>>((const float*)n->W1, n->H0, n->H1, (n->H0 + tc::KBLK - 1) / tc::KBLK, w.Bimg);
-        }
+        const int nkb = (n->H0 + 1 + tc::KB - 1) / tc::KB;
+        tc::prep_w1_kernel<<<64, 256, 0, st>>>((const float*)n->W1, (const float*)n->b1, n->H0, n->H1, nkb,
+                                                const_cast<unsigned char*>(w.im.W1img));
+        if (DA + 2 <= 8)
+            tc::prep_w0_kernel<8><<<64, 256, 0, st>>>((const float*)n->W0, (const float*)n->b0, (const float*)n->mask0,
+                                                       n->P, n->H0, DA + 1, const_cast<unsigned char*>(w.im.W0img));
+        else
+            tc::prep_w0_kernel<16><<<64, 256, 0, st>>>((const float*)n->W0, (const float*)n->b0, (const float*)n->mask0,
+                                                        n->P, n->H0, DA + 1, const_cast<unsigned char*>(w.im.W0img));
+        tc::prep_w2_kernel<<<64, 256, 0, st>>>((const float*)n->W2, (const float*)n->mask1, n->P, n->H1, D, D <= 4 ? 4 : 8,
+                                                const_cast<float*>(w.im.W2p));
     }
     return cudaGetLastError();
 }
@@ -488,39 +475,24 @@ static cudaError_t launch_mlp_simt(const BnnMlpArgs<T>& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 template <int GEO, bool TAN>
-static cudaError_t launch_mlp_tc(const BnnMlpArgs<float>& a, const float* Bimg, cudaStream_t st) {
-    constexpr int RPP = TAN ? Geo<GEO>::D + 2 : 1, NPART = 4 * (32 / RPP);
-    auto kern = tc::bnn_mlp_tc_kernel<GEO, TAN>;
-    const int smem = tc::Smem::TOTAL + 1024;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    const long long ntiles = (a.total + NPART - 1) / NPART;
-    const int grid = (int)(ntiles < (long long)num_sms() ? ntiles : (long long)num_sms());
-    kern<<<grid, tc::THREADS, smem, st>>>(a, Bimg, (a.net.H0 + tc::KBLK - 1) / tc::KBLK);
-    return cudaGetLastError();
-}
-template <int GEO, bool TAN>
-static cudaError_t launch_mlp_tc2(const BnnMlpArgs<float>& a, const tc2::Images& im, cudaStream_t st) {
+static cudaError_t launch_mlp_tc(const BnnMlpArgs<float>& a, const tc::Images& im, cudaStream_t st) {
     typedef Geo<GEO> G;
     constexpr int K0P = G::DA + G::NU + 1 <= 8 ? 8 : 16, DP = G::D <= 4 ? 4 : 8;
-    auto kern = tc2::bnn_mlp_tc2_kernel<GEO, TAN>;
-    const int smem = tc2::Cfg<K0P, DP>::TOTAL + tc2::Cfg<K0P, DP>::ALIGN_PAD;
+    auto kern = tc::bnn_mlp_tc_kernel<GEO, TAN>;
+    const int smem = tc::Cfg<K0P, DP>::TOTAL + tc::Cfg<K0P, DP>::ALIGN_PAD;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const int S = (int)(a.total / a.net.P);                  // items per particle: (problem, alpha) pairs / problems
-    const int tiles_p = (S + tc2::TILE_M - 1) / tc2::TILE_M;      // super-tiles per particle (TAN: 1 + T passes each)
+    const int tiles_p = (S + tc::TILE_M - 1) / tc::TILE_M;      // super-tiles per particle (TAN: 1 + T passes each)
     const long long ntiles = (long long)tiles_p * a.net.P;
     const int grid = (int)(ntiles < (long long)num_sms() ? ntiles : (long long)num_sms());
-    kern<<<grid, tc2::THREADS, smem, st>>>(a, im, S, tiles_p, (a.net.H0 + 1 + tc2::KB - 1) / tc2::KB);
+    kern<<<grid, tc::THREADS, smem, st>>>(a, im, S, tiles_p, (a.net.H0 + 1 + tc::KB - 1) / tc::KB);
     return cudaGetLastError();
 }
 template <class T, int GEO, bool TAN>
-static cudaError_t launch_mlp(const BnnMlpArgs<T>& a, const float* Bimg, const tc2::Images& im, cudaStream_t st) {
+static cudaError_t launch_mlp(const BnnMlpArgs<T>& a, const tc::Images& im, cudaStream_t st) {
     if (use_tensor_cores<T>(a.net.H0, a.net.H1)) {
-        if constexpr (sizeof(T) == 4) {
-            if (use_tc_v2(a.net.H0, a.net.H1)) return launch_mlp_tc2<GEO, TAN>(a, im, st);
-            return launch_mlp_tc<GEO, TAN>(a, Bimg, st);
-        }
+        if constexpr (sizeof(T) == 4) return launch_mlp_tc<GEO, TAN>(a, im, st);
     }
     const int H = a.net.H0 > a.net.H1 ? a.net.H0 : a.net.H1;
     if (H <= 32) return launch_mlp_simt<T, GEO, TAN, 2>(a, st);
@@ -589,7 +561,7 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
                                                                   (const T*)c.u_max, w.ucur, (T*)c.L_u);
         a.X = cur; a.Xn = nxt;
         prof_begin(PROF_MLP_LIN, c.st);
-        CK((launch_mlp<T, GEO, true>(a, w.Bimg, w.im, c.st)));
+        CK((launch_mlp<T, GEO, true>(a, w.im, c.st)));
         prof_end(PROF_MLP_LIN, c.st);
         m.t = t; m.X = cur; m.Xn = nxt;
         prof_begin(PROF_MOMENT_LIN, c.st);
@@ -649,7 +621,7 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     for (int t = 0; t < N; ++t) {
         a.X = cur; a.Xn = nxt;
         prof_begin(PROF_MLP_ROLL, c.st);
-        CK((launch_mlp<T, GEO, false>(a, w.Bimg, w.im, c.st)));
+        CK((launch_mlp<T, GEO, false>(a, w.im, c.st)));
         prof_end(PROF_MLP_ROLL, c.st);
         r.t = t; r.Xn = nxt;
         prof_begin(PROF_ROLL_STEP, c.st);

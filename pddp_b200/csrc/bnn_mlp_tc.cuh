@@ -1,36 +1,41 @@
 // Particle MLP on the 5th-generation tensor cores (tcgen05 + TMEM), fp32 in / fp32 out.
 //
-// The 200x200 hidden layer -- the only dense contraction on the PDDP hot path -- runs as
-// tcgen05.mma.kind::tf32 with the accumulator in tensor memory.  Plain TF32 (10-bit mantissa) moves
-// the feedback gains by ~1e-2 relative (measured), so every operand is split into
-// hi + lo TF32 parts and three MMAs (hi*hi + lo*hi + hi*lo) recover fp32-class accuracy ("3xTF32").
+//   X'_p = X_p + dX_std * fc_out(relu(M1_p * fc_1(relu(M0_p * fc_0(norm([aug(X_p), u])))))) + dX_mean
+//   (ref: pddp/models/bnn/modules.py:200-264, 774-789; dropout masks are [P,H], one row per particle)
+// and, for the linearisation, its Jacobian w.r.t. (X_p, u) by forward-mode tangents that share the
+// primal's activation pattern.
 //
-// Persistent kernel, one CTA per SM, 10 warps, warp-specialised:
-//   warps 0-3  epilogue : tcgen05.ld of the 128x208 accumulator (one row per thread), bias + dropout
-//                         mask + ReLU, tangent rows follow their primal's activation pattern via
-//                         __ballot_sync (a particle's 1+T rows sit in one warp), output layer
-//                         H1 -> D on the CUDA cores, X' and dX'/d(X,u) stored to global.
-//   warps 4-7  producer : layer 0 (K0 <= 9 inputs) on the CUDA cores for one row per thread, one
-//                         32-column K-block at a time, hi/lo split, written to shared memory in the
-//                         UMMA K-major SWIZZLE_128B layout (the A operand).
-//   warp  8    loader   : streams the pre-swizzled hi/lo images of W1 (the B operand, L2 resident)
-//                         with cp.async.bulk + mbarrier complete_tx, one K-block per stage.
-//   warp  9    issuer   : one thread issues 4 x 3 tcgen05.mma per K-block and tcgen05.commit's the
-//                         stage-empty / accumulator-full barriers.
-// Two A/B stages and two TMEM accumulator stages (2 x 256 columns) overlap producer, MMA and
-// epilogue across K-blocks and tiles.
+// Design (measurements and the road here: profiles/r1_summary.md):
+//   * a tile holds 128 items of ONE particle p (rows gathered with stride P), so the dropout masks
+//     are per-column constants of the tile: M0_p is folded into a per-particle image of W0|b0
+//     (relu(m*x) = m*relu(x), m >= 0) and M1_p into a per-particle copy of the output weights --
+//     no mask is read in the inner loops;
+//   * layer 0 runs on the tensor core too: A0 = [norm(aug(X),u), 1] (K padded to 8/16) times the
+//     per-particle image, 3xTF32, 32 hidden units at a time into a small TMEM accumulator.  Row
+//     H0 of the image is the unit vector of the bias column, so hidden unit H0 is the constant 1
+//     that carries b1 through the second GEMM (b1 is column H0 of the W1 image);
+//   * layer 1 (the 200x200 contraction) is TF32 x TF32 plus ONE BF16 pass over K = 32 for both
+//     cross terms ([a_lo | a_hi] . [b_hi | b_lo]): fp32-class accuracy for two tensor passes;
+//   * tangents are pass-major: a super-tile is the primal pass followed by one pass per direction
+//     over the same 128 items, so a thread meets the primal and the tangent pre-activation of the
+//     same (item, hidden unit) and the ReLU gate is a register bit mask, never a shuffle;
+//   * two independent tile "tracks" per CTA consume the same streamed W1 K-block (16 wide,
+//     SWIZZLE_64B): half the L2->smem traffic per row.  Track 1 runs half a tile behind track 0,
+//     and each track has its own layer-1 issuer thread, so one track's epilogue is covered by the
+//     other's MMAs (they can drift NB W1 stages apart);
+//   * warp roles (20 warps): per track 4 epilogue warps (16x256b TMEM fragments, output layer on
+//     the CUDA cores with quad-shuffle column sums), 4 mid-stage warps (tcgen05.ld of the layer-0
+//     chunk, ReLU / gate, hi-lo split, st.shared into the UMMA K-major layout) and one layer-1
+//     MMA-issuer thread; one polling layer-0 issuer thread for both tracks; one bulk-copy loader.
+//
+// TMEM (512 columns): track t owns columns [256t, 256t+208) for the layer-1 accumulator and
+// [256t+208, 256t+240) for the layer-0 chunk.
 #pragma once
 #include "bnn_mlp_simt.cuh"
+#include <cuda_bf16.h>
 
 namespace pddp {
 namespace tc {
-
-constexpr int TILE_M = 128, TILE_N = 208, KBLK = 32, MAX_KB = 7, STAGES = 2;
-constexpr int A_PART_BYTES = TILE_M * 128;            // 16 KB  (128 rows x 32 tf32)
-constexpr int B_PART_BYTES = TILE_N * 128;            // 26 KB  (208 rows x 32 tf32)
-constexpr int A_STAGE_BYTES = 2 * A_PART_BYTES;       // hi | lo
-constexpr int B_STAGE_BYTES = 2 * B_PART_BYTES;       // hi | lo
-constexpr int THREADS = 320;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,106 +73,272 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
         "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+
+constexpr int TILE_M = 128, TILE_N = 208, KB = 16, MAX_NKB = 13, MAX_NCH = 7, N0 = 32;
+// Layer 1 computes a*b ~ a_hi*b_hi (TF32 x TF32) + [a_lo | a_hi] * [b_hi | b_lo] (BF16, K = 32): the two
+// cross terms are 2^-11 of the product, so 8-bit operands keep them to ~2^-20 -- fp32-class
+// accuracy for two tensor-core passes instead of the three of 3xTF32, and a third less operand
+// traffic from shared memory (the kernel is bound by the shared-memory data pipe, profiles/).
+constexpr int B_PART = TILE_N * 64;    // W1 K-block, part 0: 208 rows x 16 tf32 (hi); part 1: 208 rows x 32 bf16 [hi | lo]
+constexpr int B_STAGE = 2 * B_PART;    // 26 624 B
+constexpr int A1_PART = TILE_M * 64;   // part 0: 128 rows x 16 tf32 (hi); part 1: 128 rows x 32 bf16 [lo | hi]
+constexpr int A1_SLOT = 2 * A1_PART;   // 16 384 B
+constexpr int THREADS = 20 * 32;
+constexpr int TM_ACC1 = 0, TM_ACC0 = 208, TM_TRACK = 256;
+
+// byte offset of element (row, kk) in a K-major tile whose rows are ROWB bytes (32 / 64 / 128 =
+// SWIZZLE_32B / 64B / 128B): 16-byte chunk index XORed with the matching bits of the row index.
+template <int ROWB>
+__host__ __device__ __forceinline__ uint32_t swz(int row, int kk) {
+    constexpr int SH = ROWB == 32 ? 2 : ROWB == 64 ? 1 : 0;
+    const int chunk = (kk >> 2) ^ ((row & 7) >> SH);
+    return (uint32_t)((row >> 3) * (8 * ROWB) + (row & 7) * ROWB + (chunk << 4) + (kk & 3) * 4);
+}
+// K-major shared-memory descriptor for rows of ROWB bytes (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) addr>>4, [16,30) LBO>>4 = 1, [32,46) SBO>>4 = 8 rows, [46,48) version 1, [61,64) layout type.
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    constexpr uint64_t LT = ROWB == 32 ? 6 : ROWB == 64 ? 4 : 2;
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= LT << 61;
+    return d;
+}
+constexpr uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// hi = x rounded to TF32 (round half away, like cvt.rna), lo = (x - hi) truncated to TF32
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
+}
+
+// two floats -> packed bf16x2 (a in the low half = lower address)
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float x, float y, float z, float w) {
+    sts128(addr, __float_as_uint(x), __float_as_uint(y), __float_as_uint(z), __float_as_uint(w));
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate) : "memory");
+}
+constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+// 16 lanes x 256 bit fragments: register 4i+{0,1} = row lane/4, columns 8i + 2*(lane%4) + {0,1};
+// register 4i+{2,3} = row lane/4 + 8, same columns (measured with tools/probe/tmem_layout.cu).
+__device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) addr>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4 = 1024 B between
-// 8-row groups, [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
+__device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int e = 8; e < 16; ++e) r[e] = 0;
 }
-// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major A and B,
-// N>>3 @17, M>>4 @24.
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled
+// above the wait.
+__device__ __forceinline__ void tc_wait_ld16(float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+__device__ __forceinline__ void tc_wait_ld32(float* v) {
+    tc_wait_ld16(v);
+    tc_wait_ld16(v + 16);
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
-// byte offset of element (row, kk) inside a [rows][32 x tf32] K-major SWIZZLE_128B tile
-__host__ __device__ __forceinline__ uint32_t swz_offset(int row, int kk) {
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ (row & 7)) & 7) << 4) + (kk & 3) * 4);
-}
-
-struct Smem {
-    static constexpr int A_OFF = 0;
-    static constexpr int B_OFF = A_OFF + STAGES * A_STAGE_BYTES;          // 65536
-    static constexpr int W0_OFF = B_OFF + STAGES * B_STAGE_BYTES;         // + 106496
-    static constexpr int W0_BYTES = TILE_N * 12 * 4;                      // sW0[c][12], k < K0 <= 9 (float4 reads)
-    static constexpr int B0_OFF = W0_OFF + W0_BYTES;
-    static constexpr int B1_OFF = B0_OFF + TILE_N * 4;
-    static constexpr int W2_OFF = B1_OFF + TILE_N * 4;                    // W2s[c][8]
-    static constexpr int BAR_OFF = W2_OFF + TILE_N * 8 * 4;
-    static constexpr int TOTAL = BAR_OFF + 16 * 8 + 16;
+template <int K0P, int DP>
+struct Cfg {
+    static constexpr int NB = K0P == 8 ? 3 : 2;    // W1 K-block stages
+    static constexpr int NS = K0P == 8 ? 3 : 2;    // layer-1 A-operand slots per track
+    static constexpr int ROWB0 = K0P * 4;          // layer-0 operand row pitch (SWIZZLE_32B / 64B)
+    static constexpr int A0_PART = TILE_M * ROWB0, A0_BYTES = 2 * A0_PART;
+    static constexpr int W0_CHUNK_PART = N0 * ROWB0, W0_CHUNK = 2 * W0_CHUNK_PART, W0_BYTES = MAX_NCH * W0_CHUNK;
+    static constexpr int W2_BYTES = TILE_N * DP * 4;
+    static constexpr int B_OFF = 0;
+    static constexpr int A1_OFF = B_OFF + NB * B_STAGE;
+    static constexpr int A0_OFF = A1_OFF + 2 * NS * A1_SLOT;
+    static constexpr int W0_OFF = A0_OFF + 2 * A0_BYTES;
+    static constexpr int W2_OFF = W0_OFF + 2 * W0_BYTES;
+    static constexpr int BAR_OFF = W2_OFF + 2 * W2_BYTES;
+    static constexpr int NBARS = 2 * NB + 4 * NS + 14;
+    static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
+    static constexpr int ALIGN_PAD = 512;
 };
 
-// Image of W1 for the loader: [kb][hi|lo][208 rows x 128 B swizzled]; zero padded.
-__global__ void bnn_tc_prep_kernel(const float* W1 /*[H1][H0]*/, int H0, int H1, int nkb, float* img) {
-    const int total = nkb * TILE_N * KBLK;
+// ---- one-time images (global memory, L2 resident) -------------------------------------------
+// W1 image: [nkb][hi|lo][208 rows x 16 k] SWIZZLE_64B; column H0 carries b1.
+__global__ void prep_w1_kernel(const float* W1 /*[H1][H0]*/, const float* b1, int H0, int H1, int nkb, unsigned char* img) {
+    const int total = nkb * TILE_N * KB;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int kb = i / (TILE_N * KBLK), rem = i - kb * TILE_N * KBLK;
-        const int n = rem / KBLK, kk = rem - n * KBLK, k = kb * KBLK + kk;
-        const float w = (n < H1 && k < H0) ? W1[(size_t)n * H0 + k] : 0.f;
-        const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
-        char* base = reinterpret_cast<char*>(img) + (size_t)kb * B_STAGE_BYTES;
-        *reinterpret_cast<float*>(base + swz_offset(n, kk)) = hi;
-        *reinterpret_cast<float*>(base + B_PART_BYTES + swz_offset(n, kk)) = lo;
+        const int kb = i / (TILE_N * KB), rem = i - kb * TILE_N * KB;
+        const int n = rem / KB, kk = rem - n * KB, k = kb * KB + kk;
+        float w = 0.f;
+        if (n < H1) w = k < H0 ? W1[(size_t)n * H0 + k] : (k == H0 ? b1[n] : 0.f);
+        const float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);
+        unsigned char* base = img + (size_t)kb * B_STAGE;
+        *reinterpret_cast<float*>(base + swz<64>(n, kk)) = hi;
+        // bf16 part: element kk of [hi | lo] sits at 2-byte index kk (hi) or 16 + kk (lo) of the 64-byte row
+        unsigned char* b2 = base + B_PART + (n >> 3) * 512 + (n & 7) * 64;
+        const int sw = (n >> 1) & 3;
+        *reinterpret_cast<__nv_bfloat16*>(b2 + ((((kk >> 3)) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(w);
+        *reinterpret_cast<__nv_bfloat16*>(b2 + (((2 + (kk >> 3)) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(w - hi);
+    }
+}
+// Per-particle layer-0 image: [P][chunk][hi|lo][32 rows x K0P]; row n < H0 is m0[p][n]*[W0[n][:], b0[n]],
+// row H0 is the unit vector of the bias column (the constant-1 hidden unit), the rest zero.
+template <int K0P>
+__global__ void prep_w0_kernel(const float* W0 /*[H0][K0]*/, const float* b0, const float* mask0 /*[P][H0]*/, int P,
+                               int H0, int K0, unsigned char* img) {
+    typedef Cfg<K0P, 4> C;
+    const int total = P * MAX_NCH * N0 * K0P;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int p = i / (MAX_NCH * N0 * K0P), rem = i - p * (MAX_NCH * N0 * K0P);
+        const int j = rem / (N0 * K0P), rem2 = rem - j * (N0 * K0P);
+        const int rr = rem2 / K0P, k = rem2 - rr * K0P, n = j * N0 + rr;
+        float w = 0.f;
+        if (n < H0) w = mask0[(size_t)p * H0 + n] * (k < K0 ? W0[(size_t)n * K0 + k] : (k == K0 ? b0[n] : 0.f));
+        else if (n == H0) w = k == K0 ? 1.f : 0.f;
+        float hi, lo;
+        split_tf32(w, hi, lo);
+        unsigned char* base = img + (size_t)p * C::W0_BYTES + (size_t)j * C::W0_CHUNK;
+        *reinterpret_cast<float*>(base + swz<C::ROWB0>(rr, k)) = hi;
+        *reinterpret_cast<float*>(base + C::W0_CHUNK_PART + swz<C::ROWB0>(rr, k)) = lo;
+    }
+}
+// Per-particle output weights: W2p[p][c][o] = m1[p][c] * W2[o][c]  (mean head only, o < D)
+__global__ void prep_w2_kernel(const float* W2 /*[2D][H1]*/, const float* mask1 /*[P][H1]*/, int P, int H1, int D, int DP,
+                               float* out) {
+    const int total = P * TILE_N * DP;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int p = i / (TILE_N * DP), rem = i - p * (TILE_N * DP);
+        const int c = rem / DP, o = rem - c * DP;
+        out[i] = (c < H1 && o < D) ? mask1[(size_t)p * H1 + c] * W2[(size_t)o * H1 + c] : 0.f;
     }
 }
 
+struct Images {
+    const unsigned char* W1img;
+    const unsigned char* W0img;
+    const float* W2p;
+};
+
 template <int GEO, bool TAN>
-__global__ void __launch_bounds__(THREADS, 1) bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const float* __restrict__ Bimg, int nkb) {
+__global__ void __launch_bounds__(THREADS, 1)
+bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p, int nkb) {
     typedef Geo<GEO> G;
     constexpr int D = G::D, DA = G::DA, NNA = G::NNA, NANG = G::NANG, K0 = DA + G::NU;
-    constexpr int TD = TAN ? D + G::NU : 0, RPP = 1 + TD, PPW = 32 / RPP, NPART = 4 * PPW;
-    extern __shared__ __align__(1024) unsigned char smem[];
-    float* sW0 = reinterpret_cast<float*>(smem + Smem::W0_OFF);
-    float* sb0 = reinterpret_cast<float*>(smem + Smem::B0_OFF);
-    float* sb1 = reinterpret_cast<float*>(smem + Smem::B1_OFF);
-    float* sW2 = reinterpret_cast<float*>(smem + Smem::W2_OFF);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BAR_OFF);
-    uint64_t *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 6, *acc_full = bars + 8,
-             *acc_empty = bars + 10;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    constexpr int K0P = K0 + 1 <= 8 ? 8 : 16, DP = D <= 4 ? 4 : 8;
+    typedef Cfg<K0P, DP> C;
+    constexpr int NB = C::NB, NS = C::NS, ROWB0 = C::ROWB0;
+    constexpr int TD = TAN ? D + G::NU : 0, RPP = 1 + TD;     // passes per super-tile: primal + one per tangent direction
+    constexpr uint32_t IDESC1 = idesc_tf32(TILE_M, TILE_N), IDESC1B = idesc_bf16(TILE_M, TILE_N), IDESC0 = idesc_tf32(TILE_M, N0);
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + C::ALIGN_PAD - 1) & ~(uintptr_t)(C::ALIGN_PAD - 1));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+    uint64_t* b_full = bars;                 // [NB]
+    uint64_t* b_empty = b_full + NB;         // [NB]
+    uint64_t* a1_full = b_empty + NB;        // [2][NS]
+    uint64_t* a1_empty = a1_full + 2 * NS;   // [2][NS]
+    uint64_t* acc0_full = a1_empty + 2 * NS; // [2]
+    uint64_t* acc0_empty = acc0_full + 2;
+    uint64_t* a0_full = acc0_empty + 2;
+    uint64_t* acc1_full = a0_full + 2;
+    uint64_t* acc1_empty = acc1_full + 2;
+    uint64_t* w0_full = acc1_empty + 2;
+    uint64_t* w2_full = w0_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBARS);
+
     const BnnNet<float>& n = a.net;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int H0 = n.H0, H1 = n.H1, P = n.P;
-    const long long ntiles = (a.total + NPART - 1) / NPART;
+    const int P = n.P;
 
-    // ---- one-time setup ----
-    for (int i = tid; i < 12 * TILE_N; i += THREADS) {
-        const int c = i / 12, k = i - c * 12;
-        sW0[i] = (k < K0 && c < H0) ? n.W0T[k * H0 + c] : 0.f;
-    }
-    for (int i = tid; i < TILE_N; i += THREADS) {
-        sb0[i] = i < H0 ? n.b0[i] : 0.f;
-        sb1[i] = i < H1 ? n.b1[i] : 0.f;
-    }
-    for (int i = tid; i < TILE_N * 8; i += THREADS) {
-        const int c = i >> 3, o = i & 7;
-        sW2[i] = (c < H1 && o < D) ? n.W2T[c * D + o] : 0.f;
-    }
+    // ---- tile schedule.  A super-tile is 128 items (rollout: (problem, alpha) pairs; linearise:
+    // problems) of one particle; it is RPP consecutive MMA tiles ("passes") on one track: the primal
+    // rows, then one pass per tangent direction -- so a thread sees the primal and the tangent
+    // pre-activations of the same (item, hidden unit) and the ReLU gate never crosses lanes.
+    // Each CTA owns a contiguous range of super-tiles; track t takes every other one.  Track 1 is
+    // `skew` K-blocks behind track 0 in the W1 stream.
+    const long long NT = (long long)P * tiles_p;
+    const long long T0 = NT * blockIdx.x / gridDim.x, T1 = NT * (blockIdx.x + 1) / gridDim.x;
+    const int cnt = (int)(T1 - T0);
+    const int ntl[2] = {((cnt + 1) / 2) * RPP, (cnt / 2) * RPP};     // MMA tiles per track
+    const int skew = (nkb / 2) & ~1;
+    const int nch = (nkb + 1) / 2;
+    const uint32_t w0_bytes = (uint32_t)nch * C::W0_CHUNK;
+    const int len0 = ntl[0] * nkb, len1 = ntl[1] ? skew + ntl[1] * nkb : 0;
+    const int nblk = len0 > len1 ? len0 : len1;          // W1 K-blocks this CTA streams
+
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&a_full[s], 128);
-            mbar_init(&a_empty[s], 1);
-            mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], 1);
-            mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 128);
+        for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2); }   // both tracks release a W1 stage
+        for (int s = 0; s < 2 * NS; ++s) { mbar_init(&a1_full[s], 128); mbar_init(&a1_empty[s], 1); }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&acc0_full[t], 1);
+            mbar_init(&acc0_empty[t], 128);
+            mbar_init(&a0_full[t], 128);
+            mbar_init(&acc1_full[t], 1);
+            mbar_init(&acc1_empty[t], 128);
+            mbar_init(&w0_full[t], 1);
+            mbar_init(&w2_full[t], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -180,193 +351,385 @@ __global__ void __launch_bounds__(THREADS, 1) bnn_mlp_tc_kernel(const BnnMlpArgs
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 4 && warp < 8) {
-        // ================= producer: layer 0 -> A operand =================
-        const int r = tid - 128, w = r >> 5, ql = lane / RPP, d = lane - ql * RPP;
-        const int q = w * PPW + ql;
-        uint32_t kcount = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const long long g = tile * NPART + q;
-            const bool valid = ql < PPW && g < a.total;
-            float ap[K0], da[K0];
-#pragma unroll
-            for (int k = 0; k < K0; ++k) { ap[k] = 0.f; da[k] = 0.f; }
-            const float* m0 = n.mask0;
-            if (valid) {
-                float x[D], in[K0], sc[K0];
-#pragma unroll
-                for (int i = 0; i < D; ++i) x[i] = a.X[g * D + i];
-#pragma unroll
-                for (int k = 0; k < K0; ++k) sc[k] = n.X_std_inv ? n.X_std_inv[k] : 1.f;
-#pragma unroll
-                for (int i = 0; i < NNA; ++i) in[i] = x[G::nonang(i)];
-#pragma unroll
-                for (int i = 0; i < NANG; ++i) { in[NNA + 2 * i] = sinf(x[G::ang(i)]); in[NNA + 2 * i + 1] = cosf(x[G::ang(i)]); }
-                in[DA] = a.u[g / P];
-#pragma unroll
-                for (int k = 0; k < K0; ++k) ap[k] = (in[k] - (n.X_mean ? n.X_mean[k] : 0.f)) * sc[k];
-                if (TAN && d > 0) {
-                    const int dir = d - 1;
-#pragma unroll
-                    for (int i = 0; i < NNA; ++i) if (dir == G::nonang(i)) da[i] = sc[i];
-#pragma unroll
-                    for (int i = 0; i < NANG; ++i) if (dir == G::ang(i)) {
-                        da[NNA + 2 * i] = in[NNA + 2 * i + 1] * sc[NNA + 2 * i];
-                        da[NNA + 2 * i + 1] = -in[NNA + 2 * i] * sc[NNA + 2 * i + 1];
-                    }
-                    if (dir == D) da[DA] = sc[DA];
-                }
-                m0 = n.mask0 + (size_t)(g % P) * H0;
+    if (warp == 18) {
+        // ================= loader: W1 K-blocks, shared by both tracks =================
+        if (lane == 0) {
+            uint32_t s = 0, ph = 1, kb = 0;
+            for (int nb = 0; nb < nblk; ++nb) {
+                mbar_wait(&b_empty[s], ph);
+                mbar_expect_tx(&b_full[s], B_STAGE);
+                bulk_g2s(smem + C::B_OFF + s * B_STAGE, im.W1img + (size_t)kb * B_STAGE, B_STAGE, &b_full[s]);
+                if (++s == NB) { s = 0; ph ^= 1; }
+                if (++kb == (uint32_t)nkb) kb = 0;
             }
-            for (int kb = 0; kb < nkb; ++kb, ++kcount) {
-                const int s = kcount & 1;
-                mbar_wait(&a_empty[s], ((kcount >> 1) & 1) ^ 1);
-                unsigned char* Ahi = smem + Smem::A_OFF + s * A_STAGE_BYTES;
-                unsigned char* Alo = Ahi + A_PART_BYTES;
+        }
+    } else if (warp == 19) {
+        // ================= layer-0 issuer (one thread, both tracks, polling): chunk c+1 of a track is
+        // issued the moment its mid-stage has drained chunk c, independent of where layer 1 stands ====
+        if (lane == 0) {
+            uint32_t l0cnt[2] = {0, 0}, w0loads[2] = {0, 0};
+            int curp[2] = {-1, -1}, k[2] = {0, 0}, pos[2] = {0, 0};
+            bool fresh[2] = {true, true};          // next chunk is the first of its tile
+            while (k[0] < ntl[0] || k[1] < ntl[1]) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float hi[4], lo[4], mk4[4];
-                    // this row's dropout-mask values for 4 columns: one LDG.128 (H0 % 4 == 0 checked on the host)
-                    if (valid && kb * KBLK + j * 4 < H0)
-                        *reinterpret_cast<float4*>(mk4) = __ldg(reinterpret_cast<const float4*>(m0 + kb * KBLK + j * 4));
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int c = kb * KBLK + j * 4 + e;
-                        float v = 0.f;
-                        if (valid && c < H0) {
-                            float wk[12];
-#pragma unroll
-                            for (int k4 = 0; k4 < (K0 + 3) / 4; ++k4)
-                                *reinterpret_cast<float4*>(wk + 4 * k4) = *reinterpret_cast<const float4*>(sW0 + c * 12 + 4 * k4);
-                            float pre = sb0[c];
-#pragma unroll
-                            for (int k = 0; k < K0; ++k) pre += ap[k] * wk[k];
-                            const float mk = mk4[e];
-                            const float pm = pre * mk;
-                            if (!TAN || d == 0) v = pm > 0.f ? pm : 0.f;
-                            else if (pm > 0.f) {
-                                float dp = 0.f;
-#pragma unroll
-                                for (int k = 0; k < K0; ++k) dp += da[k] * wk[k];
-                                v = dp * mk;
-                            }
+                for (int t = 0; t < 2; ++t) {
+                    if (k[t] >= ntl[t]) continue;
+                    if (fresh[t]) {
+                        const int p = (int)((T0 + 2 * (k[t] / RPP) + t) / tiles_p);
+                        if (p != curp[t]) {
+                            if (!mbar_test(&w0_full[t], w0loads[t] & 1)) continue;
+                            ++w0loads[t];
+                            curp[t] = p;
                         }
-                        hi[e] = tf32_rna(v);
-                        lo[e] = tf32_rna(v - hi[e]);
+                        if (!mbar_test(&a0_full[t], (uint32_t)k[t] & 1)) continue;
+                        fresh[t] = false;
                     }
-                    const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((j ^ (r & 7)) & 7) << 4));
-                    *reinterpret_cast<float4*>(Ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    if (!mbar_test(&acc0_empty[t], (l0cnt[t] & 1) ^ 1)) continue;
+                    tc_fence_after();
+                    int kb = t * skew + pos[t];
+                    if (kb >= nkb) kb -= nkb;
+                    const int nk = kb + 1 < nkb ? 2 : 1, j = kb >> 1;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC0);
+                    const uint32_t a0 = smem_u32(smem + C::A0_OFF + t * C::A0_BYTES);
+                    const uint32_t b0 = smem_u32(smem + C::W0_OFF + t * C::W0_BYTES + j * C::W0_CHUNK);
+                    const uint64_t ahi = make_desc<ROWB0>(a0), alo = make_desc<ROWB0>(a0 + C::A0_PART);
+                    const uint64_t bhi = make_desc<ROWB0>(b0), blo = make_desc<ROWB0>(b0 + C::W0_CHUNK_PART);
+#pragma unroll
+                    for (int ks = 0; ks < K0P / 8; ++ks) {
+                        const uint64_t o = (uint64_t)(ks * 2);
+                        tc_mma_tf32(d_tmem, ahi + o, bhi + o, IDESC0, ks != 0);
+                        tc_mma_tf32(d_tmem, alo + o, bhi + o, IDESC0, 1);
+                        tc_mma_tf32(d_tmem, ahi + o, blo + o, IDESC0, 1);
+                    }
+                    tc_commit(&acc0_full[t]);
+                    ++l0cnt[t];
+                    pos[t] += nk;
+                    if (pos[t] >= nkb) { pos[t] = 0; ++k[t]; fresh[t] = true; }
                 }
-                fence_async_smem();
-                mbar_arrive(&a_full[s]);
             }
         }
-    } else if (warp == 8) {
-        // ================= loader: W1 hi/lo images -> B operand =================
+    } else if (warp >= 16) {
+        // ================= layer-1 issuers: one thread per track (a track that waits for its epilogue
+        // or its mid-stage does not hold the other one up; they drift at most NB W1 stages apart) ====
         if (lane == 0) {
-            uint32_t kcount = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-                for (int kb = 0; kb < nkb; ++kb, ++kcount) {
-                    const int s = kcount & 1;
-                    mbar_wait(&b_empty[s], ((kcount >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&b_full[s], B_STAGE_BYTES);
-                    bulk_g2s(smem + Smem::B_OFF + s * B_STAGE_BYTES,
-                             reinterpret_cast<const char*>(Bimg) + (size_t)kb * B_STAGE_BYTES, B_STAGE_BYTES, &b_full[s]);
-                }
-        }
-    } else if (warp == 9) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t kcount = 0, it = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                mbar_wait(&acc_empty[as], ((it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
-                for (int kb = 0; kb < nkb; ++kb, ++kcount) {
-                    const int s = kcount & 1;
-                    const uint32_t ph = (kcount >> 1) & 1;
-                    mbar_wait(&a_full[s], ph);
-                    mbar_wait(&b_full[s], ph);
+            const int t = warp - 16;
+            uint32_t s = 0, bph = 0, slot = 0, sph = 0;
+            int kb = 0, k = 0, pos = 0;
+            for (int nb = 0; nb < nblk; ++nb) {
+                mbar_wait(&b_full[s], bph);
+                if (nb < t * skew || k >= ntl[t]) {
+                    mbar_arrive(&b_empty[s]);               // this track does not use the block
+                } else {
+                    if (pos == 0) mbar_wait(&acc1_empty[t], ((uint32_t)k & 1) ^ 1);
+                    mbar_wait(&a1_full[t * NS + slot], sph);
                     tc_fence_after();
-                    const uint64_t ahi = make_desc(smem_u32(smem + Smem::A_OFF + s * A_STAGE_BYTES));
-                    const uint64_t alo = make_desc(smem_u32(smem + Smem::A_OFF + s * A_STAGE_BYTES + A_PART_BYTES));
-                    const uint64_t bhi = make_desc(smem_u32(smem + Smem::B_OFF + s * B_STAGE_BYTES));
-                    const uint64_t blo = make_desc(smem_u32(smem + Smem::B_OFF + s * B_STAGE_BYTES + B_PART_BYTES));
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {      // UMMA_K = 8 tf32 = 32 B -> +2 in the >>4 address field
-                        const uint64_t o = (uint64_t)(k4 * 2);
-                        tc_mma_tf32(d_tmem, ahi + o, bhi + o, IDESC, (kb | k4) != 0);
-                        tc_mma_tf32(d_tmem, alo + o, bhi + o, IDESC, 1);
-                        tc_mma_tf32(d_tmem, ahi + o, blo + o, IDESC, 1);
-                    }
-                    tc_commit(&a_empty[s]);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC1);
+                    const uint32_t aa = smem_u32(smem + C::A1_OFF + (t * NS + slot) * A1_SLOT);
+                    const uint32_t bb = smem_u32(smem + C::B_OFF + s * B_STAGE);
+                    const uint64_t a32 = make_desc<64>(aa), a16 = make_desc<64>(aa + A1_PART);
+                    const uint64_t b32 = make_desc<64>(bb), b16 = make_desc<64>(bb + B_PART);
+                    // one UMMA K-step = 32 B of a row (8 tf32 / 16 bf16) -> +2 in the >>4 address field
+                    tc_mma_tf32(d_tmem, a32, b32, IDESC1, pos != 0);
+                    tc_mma_tf32(d_tmem, a32 + 2, b32 + 2, IDESC1, 1);
+                    tc_mma_bf16(d_tmem, a16, b16, IDESC1B, 1);          // a_lo * b_hi
+                    tc_mma_bf16(d_tmem, a16 + 2, b16 + 2, IDESC1B, 1);  // a_hi * b_lo
+                    tc_commit(&a1_empty[t * NS + slot]);
                     tc_commit(&b_empty[s]);
+                    if (pos == nkb - 1) tc_commit(&acc1_full[t]);
+                    if (++slot == NS) { slot = 0; sph ^= 1; }
+                    if (++pos == nkb) { pos = 0; ++k; }
                 }
-                tc_commit(&acc_full[as]);
+                if (++s == NB) { s = 0; bph ^= 1; }
+                if (++kb == nkb) kb = 0;
             }
         }
     } else {
-        // ================= epilogue: warps 0-3, one accumulator row per thread =================
-        const int w = warp, ql = lane / RPP, d = lane - ql * RPP, q = w * PPW + ql;
-        const int primal_lane = ql * RPP;
-        uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int as = it & 1;
-            const long long g = tile * NPART + q;
-            const bool valid = ql < PPW && g < a.total;
-            const float* m1 = n.mask1 + (valid ? (size_t)(g % P) * H1 : 0);
-            mbar_wait(&acc_full[as], (it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(as * 256);
-            float y[D];
+        // ================= worker teams: warps 0-7 epilogue (track 0, 1), warps 8-15 mid-stage =================
+        const int team = warp >> 2, t = team & 1;
+        const int r = tid & 127, w = r >> 5;                  // w = TMEM lane quarter of this warp
+        const uint32_t track_taddr = tmem_base + (uint32_t)(t * TM_TRACK);
+        const int nt = ntl[t];
+        if (nt == 0) goto done;
+        if (team >= 2) {
+            // ---------------- mid-stage (thread = row r): inputs -> A0, layer-0 accumulator -> A1 ----------------
+            const uint32_t A0 = smem_u32(smem + C::A0_OFF + t * C::A0_BYTES);
+            const uint32_t lane_taddr = track_taddr + ((uint32_t)(w * 32) << 16);
+            const uint32_t row_off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64), row_sw = (uint32_t)((r >> 1) & 3);   // SWIZZLE_64B row
+            float inc[K0], inn[K0];            // features [aug(x), u] of this row's item: current / next super-tile
+            bool vc = false, vn = false;
+            uint32_t gate[MAX_NCH];            // sign bits of the primal pre-activations, one word per chunk (TAN)
 #pragma unroll
-            for (int o = 0; o < D; ++o) y[o] = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < TILE_N; c0 += 16) {
-                float acc[16], mk16[16];
+            for (int j = 0; j < MAX_NCH; ++j) gate[j] = 0;
+            auto fetch = [&](int ks) {         // item r of super-tile ks: particle p, item i -> global row i*P + p
+                const long long tau = T0 + 2 * ks + t;
+                const int p = (int)(tau / tiles_p), l = (int)(tau - (long long)p * tiles_p);
+                const int i = l * TILE_M + r;
+                vn = i < S;
 #pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) {
-                    if (valid && c0 + 4 * e4 < H1)
-                        *reinterpret_cast<float4*>(mk16 + 4 * e4) = __ldg(reinterpret_cast<const float4*>(m1 + c0 + 4 * e4));
-                    else
-                        mk16[4 * e4] = mk16[4 * e4 + 1] = mk16[4 * e4 + 2] = mk16[4 * e4 + 3] = 0.f;
-                }
-                tc_ld16(taddr + c0, acc);
+                for (int k = 0; k < K0; ++k) inn[k] = 0.f;
+                if (vn) {
+                    float x[D];
+                    const float* xp = a.X + ((size_t)i * P + p) * D;
+                    if (D % 4 == 0) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int c = c0 + e;
-                    const float mk = mk16[e];
-                    const float pm = (acc[e] + sb1[c]) * mk;          // meaningful on primal rows
-                    float v;
-                    if (TAN) {
-                        const unsigned on = __ballot_sync(0xffffffffu, pm > 0.f);
-                        const bool act = (on >> primal_lane) & 1u;
-                        v = d == 0 ? (pm > 0.f ? pm : 0.f) : (act ? acc[e] * mk : 0.f);
+                        for (int e = 0; e < D; e += 4) *reinterpret_cast<float4*>(x + e) = __ldg(reinterpret_cast<const float4*>(xp + e));
                     } else {
-                        v = pm > 0.f ? pm : 0.f;
+#pragma unroll
+                        for (int e = 0; e < D; e += 2) *reinterpret_cast<float2*>(x + e) = __ldg(reinterpret_cast<const float2*>(xp + e));
                     }
-                    float w2[8];
 #pragma unroll
-                    for (int o4 = 0; o4 < (D + 3) / 4; ++o4)
-                        *reinterpret_cast<float4*>(w2 + 4 * o4) = *reinterpret_cast<const float4*>(sW2 + c * 8 + 4 * o4);
+                    for (int i2 = 0; i2 < NNA; ++i2) inn[i2] = x[G::nonang(i2)];
 #pragma unroll
-                    for (int o = 0; o < D; ++o) y[o] += v * w2[o];
+                    for (int i2 = 0; i2 < NANG; ++i2) { inn[NNA + 2 * i2] = sinf(x[G::ang(i2)]); inn[NNA + 2 * i2 + 1] = cosf(x[G::ang(i2)]); }
+                    inn[DA] = __ldg(a.u + i);
                 }
+            };
+            auto write_a0 = [&](int d) {       // [norm(aug(x), u), 1] (d == 0) or its tangent along direction d-1
+                float row[K0P];
+#pragma unroll
+                for (int k = 0; k < K0P; ++k) row[k] = 0.f;
+                if (vc) {
+                    float sc[K0];
+#pragma unroll
+                    for (int k = 0; k < K0; ++k) sc[k] = n.X_std_inv ? n.X_std_inv[k] : 1.f;
+                    if (!TAN || d == 0) {
+#pragma unroll
+                        for (int k = 0; k < K0; ++k) row[k] = (inc[k] - (n.X_mean ? n.X_mean[k] : 0.f)) * sc[k];
+                        row[K0] = 1.f;
+                    } else {
+                        const int dir = d - 1;
+#pragma unroll
+                        for (int i2 = 0; i2 < NNA; ++i2) if (dir == G::nonang(i2)) row[i2] = sc[i2];
+#pragma unroll
+                        for (int i2 = 0; i2 < NANG; ++i2) if (dir == G::ang(i2)) {
+                            row[NNA + 2 * i2] = inc[NNA + 2 * i2 + 1] * sc[NNA + 2 * i2];          // d sin = cos
+                            row[NNA + 2 * i2 + 1] = -inc[NNA + 2 * i2] * sc[NNA + 2 * i2 + 1];     // d cos = -sin
+                        }
+                        if (dir == D) row[DA] = sc[DA];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < K0P / 4; ++c) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split_tf32(row[4 * c + e], hi[e], lo[e]);
+                    const uint32_t off = swz<ROWB0>(r, 4 * c);
+                    sts128f(A0 + off, hi[0], hi[1], hi[2], hi[3]);
+                    sts128f(A0 + C::A0_PART + off, lo[0], lo[1], lo[2], lo[3]);
+                }
+                fence_async_smem();
+                mbar_arrive(&a0_full[t]);
+            };
+            auto load_w0 = [&](int p) {
+                mbar_expect_tx(&w0_full[t], w0_bytes);
+                bulk_g2s(smem + C::W0_OFF + t * C::W0_BYTES, im.W0img + (size_t)p * C::W0_BYTES, w0_bytes, &w0_full[t]);
+            };
+            int curp = (int)((T0 + t) / tiles_p);
+            if (r == 0) load_w0(curp);
+            fetch(0);
+#pragma unroll
+            for (int k = 0; k < K0; ++k) inc[k] = inn[k];
+            vc = vn;
+            write_a0(0);
+            uint32_t ci = 0, slot = 0, sph = 1;
+            const int kb0 = t * skew;
+            int ks = 0, d = 0;                 // super-tile and pass of the current tile
+            for (int k = 0; k < nt; ++k) {
+                const bool last_pass = d == RPP - 1;
+                if (last_pass && k + 1 < nt) fetch(ks + 1);
+                for (int pos = 0; pos < nkb;) {
+                    int kb = kb0 + pos;
+                    if (kb >= nkb) kb -= nkb;
+                    const int nk = kb + 1 < nkb ? 2 : 1, j = kb >> 1;
+                    float v[32];
+                    mbar_wait(&acc0_full[t], ci & 1);
+                    ++ci;
+                    tc_fence_after();
+                    tc_ld32(lane_taddr + TM_ACC0, v);
+                    tc_wait_ld32(v);
+                    tc_fence_before();
+                    mbar_arrive(&acc0_empty[t]);
+                    if (pos + nk >= nkb && k + 1 < nt) {
+                        // every layer-0 MMA of this tile has completed: A0 (and, between super-tiles, the W0 image) is free
+                        if (last_pass) {
+                            const int pn = (int)((T0 + 2 * (ks + 1) + t) / tiles_p);
+                            if (pn != curp) { if (r == 0) load_w0(pn); curp = pn; }
+#pragma unroll
+                            for (int k2 = 0; k2 < K0; ++k2) inc[k2] = inn[k2];
+                            vc = vn;
+                            write_a0(0);
+                        } else {
+                            write_a0(d + 1);
+                        }
+                    }
+                    if (!TAN) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+                    } else if (d == 0) {
+                        uint32_t word = 0;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            word = __funnelshift_l(__float_as_uint(v[e]), word, 1);     // sign of v[e] ends up at bit 31 - e
+                            v[e] = fmaxf(v[e], 0.f);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < MAX_NCH; ++jj) if (jj == j) gate[jj] = word;
+                    } else {
+                        uint32_t word = 0;
+#pragma unroll
+                        for (int jj = 0; jj < MAX_NCH; ++jj) if (jj == j) word = gate[jj];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = (word & (0x80000000u >> e)) ? 0.f : v[e];
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h < nk) {
+                            mbar_wait(&a1_empty[t * NS + slot], sph);
+                            const uint32_t A1 = smem_u32(smem + C::A1_OFF + (t * NS + slot) * A1_SLOT) + row_off;
+                            float hi[16], lo[16];
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                hi[e] = __uint_as_float((__float_as_uint(v[16 * h + e]) + 0x1000u) & 0xFFFFE000u);
+                                lo[e] = v[16 * h + e] - hi[e];
+                            }
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)      // part 0: hi as tf32
+                                sts128f(A1 + ((c ^ row_sw) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {    // part 1: [lo | hi] as bf16, 8 per 16-byte chunk
+                                sts128(A1 + A1_PART + ((c ^ row_sw) << 4), pack_bf16(lo[8 * c], lo[8 * c + 1]),
+                                       pack_bf16(lo[8 * c + 2], lo[8 * c + 3]), pack_bf16(lo[8 * c + 4], lo[8 * c + 5]),
+                                       pack_bf16(lo[8 * c + 6], lo[8 * c + 7]));
+                                sts128(A1 + A1_PART + (((2 + c) ^ row_sw) << 4), pack_bf16(hi[8 * c], hi[8 * c + 1]),
+                                       pack_bf16(hi[8 * c + 2], hi[8 * c + 3]), pack_bf16(hi[8 * c + 4], hi[8 * c + 5]),
+                                       pack_bf16(hi[8 * c + 6], hi[8 * c + 7]));
+                            }
+                            fence_async_smem();
+                            mbar_arrive(&a1_full[t * NS + slot]);
+                            if (++slot == NS) { slot = 0; sph ^= 1; }
+                        }
+                    }
+                    pos += nk;
+                }
+                if (++d == RPP) { d = 0; ++ks; }
             }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[as]);
-            if (valid) {
+        } else {
+            // ---------------- epilogue: layer-1 accumulator -> ReLU -> output layer -> X', dX'/d(X,u) ----------------
+            // 16x256b TMEM fragments: this thread holds rows 32w + 16hf + 8hb + lane/4 (hf, hb in {0,1}) and, of
+            // every group of 8 columns, columns 2*(lane%4) and +1 -- so one pair of LDS.128 of the output weights
+            // feeds 4 rows (a thread-per-row layout needs a broadcast LDS.128 per column: 4x the shared-memory
+            // wavefronts, and this kernel is bound by the shared-memory pipe).  Column sums are completed
+            // across the 4 lanes of a quad with two shuffles per value.
+            const uint32_t W2s = smem_u32(smem + C::W2_OFF + t * C::W2_BYTES);
+            const int q4 = lane & 3, rq = lane >> 2;
+            int curp = -1;
+            uint32_t w2loads = 0;
+            uint32_t gate[7];                  // sign bits of this thread's 208 primal pre-activations (TAN)
 #pragma unroll
-                for (int o = 0; o < D; ++o) {
-                    const float sd = n.dX_std ? n.dX_std[o] : 1.f, mn = n.dX_mean ? n.dX_mean[o] : 0.f;
-                    if (!TAN || d == 0) a.Xn[g * D + o] = a.X[g * D + o] + ((y[o] + n.b2[o]) * sd + mn);
-                    else a.Jp[(g * D + o) * TD + (d - 1)] = ((d - 1) == o ? 1.f : 0.f) + y[o] * sd;
+            for (int j = 0; j < 7; ++j) gate[j] = 0;
+            int ks = 0, d = 0;
+            for (int k = 0; k < nt; ++k) {
+                const long long tau = T0 + 2 * ks + t;
+                const int p = (int)(tau / tiles_p), l = (int)(tau - (long long)p * tiles_p);
+                if (p != curp) {
+                    named_bar_sync(1 + t, 128);      // every warp of the team is done with the old weights
+                    if (r == 0) {
+                        mbar_expect_tx(&w2_full[t], C::W2_BYTES);
+                        bulk_g2s(smem + C::W2_OFF + t * C::W2_BYTES, im.W2p + (size_t)p * TILE_N * DP, C::W2_BYTES, &w2_full[t]);
+                    }
+                    mbar_wait(&w2_full[t], w2loads & 1);
+                    ++w2loads;
+                    curp = p;
                 }
+                float y[4][D];
+#pragma unroll
+                for (int jr = 0; jr < 4; ++jr)
+#pragma unroll
+                    for (int o = 0; o < D; ++o) y[jr][o] = 0.f;
+                mbar_wait(&acc1_full[t], (uint32_t)k & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+                    constexpr int NG_MAX = 4;                                   // 8-column groups per batch
+                    const int ng = (TILE_N - c0) / 8 < NG_MAX ? (TILE_N - c0) / 8 : NG_MAX;
+                    float f[2][4 * NG_MAX];
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const uint32_t ta = track_taddr + ((uint32_t)(w * 32 + hf * 16) << 16) + TM_ACC1 + c0;
+                        if (ng == 4) tc_ld_16x256b_x4(ta, f[hf]);
+                        else tc_ld_16x256b_x2(ta, f[hf]);
+                    }
+                    tc_wait_ld16(f[0]);
+                    tc_wait_ld16(f[1]);
+#pragma unroll
+                    for (int gi = 0; gi < NG_MAX; ++gi) {
+                        if (gi < ng) {
+                            float w2[2][DP];                                    // output weights of this thread's 2 columns
+#pragma unroll
+                            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                                for (int o4 = 0; o4 < DP / 4; ++o4)
+                                    *reinterpret_cast<float4*>(&w2[cc][4 * o4]) =
+                                        lds128f(W2s + (uint32_t)(((c0 + 8 * gi + 2 * q4 + cc) * DP + 4 * o4) * 4));
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                                for (int hb = 0; hb < 2; ++hb)
+#pragma unroll
+                                    for (int cc = 0; cc < 2; ++cc) {
+                                        float vv = f[hf][4 * gi + 2 * hb + cc];
+                                        // element index of this value inside the thread's 208: fixed at compile time
+                                        const int eidx = ((c0 / 8 + gi) * 2 + hf) * 4 + 2 * hb + cc;
+                                        if (!TAN) {
+                                            vv = fmaxf(vv, 0.f);
+                                        } else if (d == 0) {
+                                            gate[eidx >> 5] = __funnelshift_l(__float_as_uint(vv), gate[eidx >> 5], 1);
+                                            vv = fmaxf(vv, 0.f);
+                                        } else {
+                                            // the sign was shifted in at position eidx%32 of its word: it sits at bit (n_w - 1 - eidx%32)
+                                            const int nw = (eidx >> 5) < 6 ? 32 : 16;
+                                            vv = (gate[eidx >> 5] & (1u << (nw - 1 - (eidx & 31)))) ? 0.f : vv;
+                                        }
+#pragma unroll
+                                        for (int o = 0; o < D; ++o) y[2 * hf + hb][o] += vv * w2[cc][o];
+                                    }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&acc1_empty[t]);
+                // complete the column sums across the quad, then lane q4 writes outputs o = q4 (and q4 + 4)
+#pragma unroll
+                for (int jr = 0; jr < 4; ++jr)
+#pragma unroll
+                    for (int o = 0; o < D; ++o) {
+                        y[jr][o] += __shfl_xor_sync(0xffffffffu, y[jr][o], 1);
+                        y[jr][o] += __shfl_xor_sync(0xffffffffu, y[jr][o], 2);
+                    }
+#pragma unroll
+                for (int oo = 0; oo < (D + 3) / 4; ++oo) {
+                    const int o = q4 + 4 * oo;
+                    if (o < D) {
+                        const float sd = n.dX_std ? n.dX_std[o] : 1.f, mn = n.dX_mean ? n.dX_mean[o] : 0.f, bo = n.b2[o];
+#pragma unroll
+                        for (int jr = 0; jr < 4; ++jr) {
+                            const int i = l * TILE_M + w * 32 + (jr >> 1) * 16 + (jr & 1) * 8 + rq;
+                            if (i < S) {
+                                float yo = 0.f;
+#pragma unroll
+                                for (int o2 = 0; o2 < D; ++o2) if (o2 == o) yo = y[jr][o2];
+                                const size_t g = (size_t)i * P + p;
+                                if (!TAN || d == 0) a.Xn[g * D + o] = __ldg(a.X + g * D + o) + ((yo + bo) * sd + mn);
+                                else a.Jp[(g * D + o) * TD + (d - 1)] = ((d - 1) == o ? 1.f : 0.f) + yo * sd;
+                            }
+                        }
+                    }
+                }
+                if (++d == RPP) { d = 0; ++ks; }
             }
         }
     }
+done:
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {

@@ -410,6 +410,7 @@ static Workspace<T> carve(void* base, const pddp_shape* s, const pddp_bnn* n, in
     w.im.W1img = reinterpret_cast<unsigned char*>(take((size_t)tc::MAX_NKB * tc::B_STAGE / sizeof(T)));
     w.im.W0img = reinterpret_cast<unsigned char*>(take(P * (size_t)tc::Cfg<16, 8>::W0_BYTES / sizeof(T)));
     w.im.W2p = reinterpret_cast<float*>(take(P * (size_t)tc::TILE_N * 8 * sizeof(float) / sizeof(T)));
+    w.im.scale = reinterpret_cast<float*>(take(256 / sizeof(T)));
     w.bytes = off;
     return w;
 }
@@ -447,8 +448,10 @@ static cudaError_t prep_weights(const pddp_shape* s, const pddp_bnn* n, const Wo
     bnn_transpose_kernel<T><<<16, 256, 0, st>>>((const T*)n->mask1, n->P, n->H1, n->P, w.m1T);
     if (use_tensor_cores<T>(n->H0, n->H1)) {
         const int nkb = (n->H0 + 1 + tc::KB - 1) / tc::KB;
-        tc::prep_w1_kernel<<<64, 256, 0, st>>>((const float*)n->W1, (const float*)n->b1, n->H0, n->H1, nkb,
-                                                const_cast<unsigned char*>(w.im.W1img));
+        tc::prep_scale_kernel<<<1, 256, 0, st>>>((const float*)n->W1, (const float*)n->b1, n->H0, n->H1,
+                                                 const_cast<float*>(w.im.scale));
+        tc::prep_w1_kernel<<<64, 256, 0, st>>>((const float*)n->W1, (const float*)n->b1, n->H0, n->H1, nkb, w.im.scale,
+                                               const_cast<unsigned char*>(w.im.W1img));
         if (DA + 2 <= 8)
             tc::prep_w0_kernel<8><<<64, 256, 0, st>>>((const float*)n->W0, (const float*)n->b0, (const float*)n->mask0,
                                                        n->P, n->H0, DA + 1, const_cast<unsigned char*>(w.im.W0img));
@@ -456,7 +459,7 @@ static cudaError_t prep_weights(const pddp_shape* s, const pddp_bnn* n, const Wo
             tc::prep_w0_kernel<16><<<64, 256, 0, st>>>((const float*)n->W0, (const float*)n->b0, (const float*)n->mask0,
                                                         n->P, n->H0, DA + 1, const_cast<unsigned char*>(w.im.W0img));
         tc::prep_w2_kernel<<<64, 256, 0, st>>>((const float*)n->W2, (const float*)n->mask1, n->P, n->H1, D, D <= 4 ? 4 : 8,
-                                                const_cast<float*>(w.im.W2p));
+                                               w.im.scale, const_cast<float*>(w.im.W2p));
     }
     return cudaGetLastError();
 }

@@ -14,13 +14,13 @@
 //     per-particle image, 3xTF32, 32 hidden units at a time into a small TMEM accumulator.  Row
 //     H0 of the image is the unit vector of the bias column, so hidden unit H0 is the constant 1
 //     that carries b1 through the second GEMM (b1 is column H0 of the W1 image);
-//   * layer 1 (the 200x200 contraction) is TF32 x TF32 plus ONE BF16 pass over K = 32 for both
-//     cross terms ([a_lo | a_hi] . [b_hi | b_lo]): fp32-class accuracy for two tensor passes;
+//   * layer 1 (the 200x200 contraction) runs in split FP16, a0*b0 + a0*b1 + a1*b0 with fp32
+//     accumulation: fp32-class accuracy from three FP16 passes and 4 operand bytes per element;
 //   * tangents are pass-major: a super-tile is the primal pass followed by one pass per direction
 //     over the same 128 items, so a thread meets the primal and the tangent pre-activation of the
 //     same (item, hidden unit) and the ReLU gate is a register bit mask, never a shuffle;
 //   * two independent tile "tracks" per CTA consume the same streamed W1 K-block (16 wide,
-//     SWIZZLE_64B): half the L2->smem traffic per row.  Track 1 runs half a tile behind track 0,
+//     SWIZZLE_64B rows of [b0 | b1]): half the L2->smem traffic per row.  Track 1 runs half a tile behind track 0,
 //     and each track has its own layer-1 issuer thread, so one track's epilogue is covered by the
 //     other's MMAs (they can drift NB W1 stages apart);
 //   * warp roles (20 warps): per track 4 epilogue warps (16x256b TMEM fragments, output layer on
@@ -32,7 +32,7 @@
 // [256t+208, 256t+240) for the layer-0 chunk.
 #pragma once
 #include "bnn_mlp_simt.cuh"
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace pddp {
 namespace tc {
@@ -75,14 +75,17 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
 }
 
 constexpr int TILE_M = 128, TILE_N = 208, KB = 16, MAX_NKB = 13, MAX_NCH = 7, N0 = 32;
-// Layer 1 computes a*b ~ a_hi*b_hi (TF32 x TF32) + [a_lo | a_hi] * [b_hi | b_lo] (BF16, K = 32): the two
-// cross terms are 2^-11 of the product, so 8-bit operands keep them to ~2^-20 -- fp32-class
-// accuracy for two tensor-core passes instead of the three of 3xTF32, and a third less operand
-// traffic from shared memory (the kernel is bound by the shared-memory data pipe, profiles/).
-constexpr int B_PART = TILE_N * 64;    // W1 K-block, part 0: 208 rows x 16 tf32 (hi); part 1: 208 rows x 32 bf16 [hi | lo]
-constexpr int B_STAGE = 2 * B_PART;    // 26 624 B
-constexpr int A1_PART = TILE_M * 64;   // part 0: 128 rows x 16 tf32 (hi); part 1: 128 rows x 32 bf16 [lo | hi]
-constexpr int A1_SLOT = 2 * A1_PART;   // 16 384 B
+// Layer 1 in split FP16: a = a0 + a1, b = b0 + b1 with a0 = fp16(a), a1 = fp16(a - a0) (22
+// significand bits together) and a*b ~ a0*b0 + a0*b1 + a1*b0 accumulated in fp32 by the tensor
+// core -- three FP16 passes of K = 16 per K-block.  That is fp32-class accuracy (the dropped a1*b1
+// is 2^-24 of the product) for 3/4 of the tensor time and 5/8..1/2 of the shared-memory and L2
+// bytes of TF32-based splitting (a 4-byte [a0 | a1] pair per element instead of 8 bytes), which
+// matters because the kernel is bound by the shared-memory data pipe (profiles/r1_summary.md).
+// FP16 range: the W1 image is scaled by a power of two so that max |w| * scale is ~2^14 (the lo
+// parts stay normal); the scale is undone inside the per-particle output weights.  Hidden
+// activations must stay below 65504 (they are O(1) for any network that rolls out finitely).
+constexpr int B_STAGE = TILE_N * 64;   // W1 K-block: 208 rows x [b0 (16 fp16) | b1 (16 fp16)], 13 312 B
+constexpr int A1_SLOT = TILE_M * 64;   // 128 rows x [a0 (16 fp16) | a1 (16 fp16)], 8 192 B
 constexpr int THREADS = 20 * 32;
 constexpr int TM_ACC1 = 0, TM_ACC0 = 208, TM_TRACK = 256;
 
@@ -116,11 +119,14 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
 }
 
-// two floats -> packed bf16x2 (a in the low half = lower address)
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+// two floats -> packed fp16x2 (a in the low half = lower address)
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
     uint32_t d;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
     return d;
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t h) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&h));
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
@@ -133,14 +139,14 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
         "r"(accumulate) : "memory");
 }
-constexpr uint32_t idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+constexpr uint32_t idesc_f16(int M, int N) {      // A, B = F16 (format 0), D = F32
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
@@ -207,8 +213,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 template <int K0P, int DP>
 struct Cfg {
-    static constexpr int NB = K0P == 8 ? 3 : 2;    // W1 K-block stages
-    static constexpr int NS = K0P == 8 ? 3 : 2;    // layer-1 A-operand slots per track
+    static constexpr int NB = K0P == 8 ? 5 : 4;    // W1 K-block stages
+    static constexpr int NS = K0P == 8 ? 6 : 4;    // layer-1 A-operand slots per track
     static constexpr int ROWB0 = K0P * 4;          // layer-0 operand row pitch (SWIZZLE_32B / 64B)
     static constexpr int A0_PART = TILE_M * ROWB0, A0_BYTES = 2 * A0_PART;
     static constexpr int W0_CHUNK_PART = N0 * ROWB0, W0_CHUNK = 2 * W0_CHUNK_PART, W0_BYTES = MAX_NCH * W0_CHUNK;
@@ -225,22 +231,45 @@ struct Cfg {
 };
 
 // ---- one-time images (global memory, L2 resident) -------------------------------------------
-// W1 image: [nkb][hi|lo][208 rows x 16 k] SWIZZLE_64B; column H0 carries b1.
-__global__ void prep_w1_kernel(const float* W1 /*[H1][H0]*/, const float* b1, int H0, int H1, int nkb, unsigned char* img) {
+// scale[0] = power of two with max(|W1|, |b1|) * scale in [2^13, 2^14]; scale[1] = 1 / scale[0]
+__global__ void prep_scale_kernel(const float* W1, const float* b1, int H0, int H1, float* scale) {
+    __shared__ float red[256];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < H0 * H1; i += blockDim.x) m = fmaxf(m, fabsf(W1[i]));
+    for (int i = threadIdx.x; i < H1; i += blockDim.x) m = fmaxf(m, fabsf(b1[i]));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int e = 0;
+        const float mx = red[0];
+        if (mx > 0.f && isfinite(mx)) { frexpf(mx, &e); e = 14 - e; }      // mx = f * 2^(e0), f in [0.5, 1)
+        e = e > 24 ? 24 : (e < -24 ? -24 : e);
+        scale[0] = ldexpf(1.f, e);
+        scale[1] = ldexpf(1.f, -e);
+    }
+}
+// W1 image: [nkb][208 rows x (b0[16] | b1[16]) fp16] SWIZZLE_64B, scaled; column H0 carries the bias b1.
+__global__ void prep_w1_kernel(const float* W1 /*[H1][H0]*/, const float* b1, int H0, int H1, int nkb,
+                               const float* scale, unsigned char* img) {
     const int total = nkb * TILE_N * KB;
+    const float sc = scale[0];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int kb = i / (TILE_N * KB), rem = i - kb * TILE_N * KB;
         const int n = rem / KB, kk = rem - n * KB, k = kb * KB + kk;
         float w = 0.f;
         if (n < H1) w = k < H0 ? W1[(size_t)n * H0 + k] : (k == H0 ? b1[n] : 0.f);
-        const float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);
-        unsigned char* base = img + (size_t)kb * B_STAGE;
-        *reinterpret_cast<float*>(base + swz<64>(n, kk)) = hi;
-        // bf16 part: element kk of [hi | lo] sits at 2-byte index kk (hi) or 16 + kk (lo) of the 64-byte row
-        unsigned char* b2 = base + B_PART + (n >> 3) * 512 + (n & 7) * 64;
+        w *= sc;
+        const __half h0 = __float2half_rn(w);
+        const __half h1 = __float2half_rn(w - __half2float(h0));
+        // element kk of [b0 | b1] sits at 2-byte index kk (b0) or 16 + kk (b1) of the 64-byte row
+        unsigned char* row = img + (size_t)kb * B_STAGE + (n >> 3) * 512 + (n & 7) * 64;
         const int sw = (n >> 1) & 3;
-        *reinterpret_cast<__nv_bfloat16*>(b2 + ((((kk >> 3)) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(w);
-        *reinterpret_cast<__nv_bfloat16*>(b2 + (((2 + (kk >> 3)) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(w - hi);
+        *reinterpret_cast<__half*>(row + (((kk >> 3) ^ sw) << 4) + (kk & 7) * 2) = h0;
+        *reinterpret_cast<__half*>(row + (((2 + (kk >> 3)) ^ sw) << 4) + (kk & 7) * 2) = h1;
     }
 }
 // Per-particle layer-0 image: [P][chunk][hi|lo][32 rows x K0P]; row n < H0 is m0[p][n]*[W0[n][:], b0[n]],
@@ -264,14 +293,15 @@ __global__ void prep_w0_kernel(const float* W0 /*[H0][K0]*/, const float* b0, co
         *reinterpret_cast<float*>(base + C::W0_CHUNK_PART + swz<C::ROWB0>(rr, k)) = lo;
     }
 }
-// Per-particle output weights: W2p[p][c][o] = m1[p][c] * W2[o][c]  (mean head only, o < D)
+// Per-particle output weights: W2p[p][c][o] = m1[p][c] * W2[o][c] / scale  (mean head only, o < D)
 __global__ void prep_w2_kernel(const float* W2 /*[2D][H1]*/, const float* mask1 /*[P][H1]*/, int P, int H1, int D, int DP,
-                               float* out) {
+                               const float* scale, float* out) {
     const int total = P * TILE_N * DP;
+    const float inv = scale[1];              // the layer-1 accumulator carries the W1 image's scale
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int p = i / (TILE_N * DP), rem = i - p * (TILE_N * DP);
         const int c = rem / DP, o = rem - c * DP;
-        out[i] = (c < H1 && o < D) ? mask1[(size_t)p * H1 + c] * W2[(size_t)o * H1 + c] : 0.f;
+        out[i] = (c < H1 && o < D) ? mask1[(size_t)p * H1 + c] * W2[(size_t)o * H1 + c] * inv : 0.f;
     }
 }
 
@@ -279,6 +309,7 @@ struct Images {
     const unsigned char* W1img;
     const unsigned char* W0img;
     const float* W2p;
+    const float* scale;        // [2]: power-of-two scale of the W1 image and its inverse
 };
 
 template <int GEO, bool TAN>
@@ -290,7 +321,7 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
     typedef Cfg<K0P, DP> C;
     constexpr int NB = C::NB, NS = C::NS, ROWB0 = C::ROWB0;
     constexpr int TD = TAN ? D + G::NU : 0, RPP = 1 + TD;     // passes per super-tile: primal + one per tangent direction
-    constexpr uint32_t IDESC1 = idesc_tf32(TILE_M, TILE_N), IDESC1B = idesc_bf16(TILE_M, TILE_N), IDESC0 = idesc_tf32(TILE_M, N0);
+    constexpr uint32_t IDESC1 = idesc_f16(TILE_M, TILE_N), IDESC0 = idesc_tf32(TILE_M, N0);
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + C::ALIGN_PAD - 1) & ~(uintptr_t)(C::ALIGN_PAD - 1));
@@ -426,13 +457,11 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC1);
                     const uint32_t aa = smem_u32(smem + C::A1_OFF + (t * NS + slot) * A1_SLOT);
                     const uint32_t bb = smem_u32(smem + C::B_OFF + s * B_STAGE);
-                    const uint64_t a32 = make_desc<64>(aa), a16 = make_desc<64>(aa + A1_PART);
-                    const uint64_t b32 = make_desc<64>(bb), b16 = make_desc<64>(bb + B_PART);
-                    // one UMMA K-step = 32 B of a row (8 tf32 / 16 bf16) -> +2 in the >>4 address field
-                    tc_mma_tf32(d_tmem, a32, b32, IDESC1, pos != 0);
-                    tc_mma_tf32(d_tmem, a32 + 2, b32 + 2, IDESC1, 1);
-                    tc_mma_bf16(d_tmem, a16, b16, IDESC1B, 1);          // a_lo * b_hi
-                    tc_mma_bf16(d_tmem, a16 + 2, b16 + 2, IDESC1B, 1);  // a_hi * b_lo
+                    const uint64_t ad = make_desc<64>(aa), bd = make_desc<64>(bb);
+                    // one UMMA K-step = 32 B of a row = 16 fp16: [x0 | x1] halves are +2 apart in the >>4 address field
+                    tc_mma_f16(d_tmem, ad, bd, IDESC1, pos != 0);     // a0 * b0
+                    tc_mma_f16(d_tmem, ad, bd + 2, IDESC1, 1);        // a0 * b1
+                    tc_mma_f16(d_tmem, ad + 2, bd, IDESC1, 1);        // a1 * b0
                     tc_commit(&a1_empty[t * NS + slot]);
                     tc_commit(&b_empty[s]);
                     if (pos == nkb - 1) tc_commit(&acc1_full[t]);
@@ -586,23 +615,18 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                         if (h < nk) {
                             mbar_wait(&a1_empty[t * NS + slot], sph);
                             const uint32_t A1 = smem_u32(smem + C::A1_OFF + (t * NS + slot) * A1_SLOT) + row_off;
-                            float hi[16], lo[16];
+                            uint32_t a0[8], a1[8];            // fp16 pairs: a0 = fp16(v), a1 = fp16(v - a0)
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) {
-                                hi[e] = __uint_as_float((__float_as_uint(v[16 * h + e]) + 0x1000u) & 0xFFFFE000u);
-                                lo[e] = v[16 * h + e] - hi[e];
+                            for (int e = 0; e < 8; ++e) {
+                                const float v0 = v[16 * h + 2 * e], v1 = v[16 * h + 2 * e + 1];
+                                a0[e] = pack_f16(v0, v1);
+                                const float2 back = unpack_f16(a0[e]);
+                                a1[e] = pack_f16(v0 - back.x, v1 - back.y);
                             }
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)      // part 0: hi as tf32
-                                sts128f(A1 + ((c ^ row_sw) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-#pragma unroll
-                            for (int c = 0; c < 2; ++c) {    // part 1: [lo | hi] as bf16, 8 per 16-byte chunk
-                                sts128(A1 + A1_PART + ((c ^ row_sw) << 4), pack_bf16(lo[8 * c], lo[8 * c + 1]),
-                                       pack_bf16(lo[8 * c + 2], lo[8 * c + 3]), pack_bf16(lo[8 * c + 4], lo[8 * c + 5]),
-                                       pack_bf16(lo[8 * c + 6], lo[8 * c + 7]));
-                                sts128(A1 + A1_PART + (((2 + c) ^ row_sw) << 4), pack_bf16(hi[8 * c], hi[8 * c + 1]),
-                                       pack_bf16(hi[8 * c + 2], hi[8 * c + 3]), pack_bf16(hi[8 * c + 4], hi[8 * c + 5]),
-                                       pack_bf16(hi[8 * c + 6], hi[8 * c + 7]));
+                            for (int c = 0; c < 2; ++c) {     // 16-byte chunks 0,1 = a0[0..7], a0[8..15]; 2,3 = a1
+                                sts128(A1 + ((c ^ row_sw) << 4), a0[4 * c], a0[4 * c + 1], a0[4 * c + 2], a0[4 * c + 3]);
+                                sts128(A1 + (((2 + c) ^ row_sw) << 4), a1[4 * c], a1[4 * c + 1], a1[4 * c + 2], a1[4 * c + 3]);
                             }
                             fence_async_smem();
                             mbar_arrive(&a1_full[t * NS + slot]);

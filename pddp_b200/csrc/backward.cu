@@ -208,11 +208,23 @@ __global__ void __launch_bounds__(128, (sizeof(T) == 4 && NZ <= 2) ? 5 : 2) back
 }
 
 // ------------------------------------------------------------------------------------------
-// warp per problem; dynamic smem: per warp 3*nz*nz + 6*nz elements
-template <class T>
-__global__ void __launch_bounds__(128) backward_warp_kernel(const BackwardArgs<T> a) {
+// A TEAM of threads per problem; dynamic smem: per team 3*nz*nz + 6*nz elements.
+//   TEAM = 32 : a warp per problem, 4 problems per CTA (nz = 14: 196 outputs per product).
+//   TEAM = 256: a CTA per problem (nz = 42: 1764 outputs x 42 MACs per product; with one warp the
+//               time loop is a chain of LDS->FMA latencies, 8 warps split every product 8 ways).
+template <int TEAM>
+__device__ __forceinline__ void team_sync() {
+    if (TEAM == 32) team_sync<TEAM>(); else __syncthreads();
+}
+template <int TEAM>
+__device__ __forceinline__ bool team_any(bool x) {
+    if (TEAM == 32) return __any_sync(0xffffffffu, x);
+    return __syncthreads_or(x) != 0;
+}
+template <class T, int TEAM>
+__global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(const BackwardArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x % TEAM, warp = threadIdx.x / TEAM, wpb = blockDim.x / TEAM;
     const int b = blockIdx.x * wpb + warp;
     if (b >= a.B) return;
     if (a.active && a.active[b] == 0) return;
@@ -225,30 +237,30 @@ __global__ void __launch_bounds__(128) backward_warp_kernel(const BackwardArgs<T
     T lo = T(0), hi = T(0);
     if (bounded) { lo = a.u_min[0]; hi = a.u_max[0]; }
 
-    for (int e = lane; e < nn; e += 32) V[e] = a.L_zz[a.lLzz.at(b, a.N, e)];
-    for (int e = lane; e < nz; e += 32) v[e] = a.L_z[a.lLz.at(b, a.N, e)];
-    __syncwarp();
+    for (int e = lane; e < nn; e += TEAM) V[e] = a.L_zz[a.lLzz.at(b, a.N, e)];
+    for (int e = lane; e < nz; e += TEAM) v[e] = a.L_z[a.lLz.at(b, a.N, e)];
+    team_sync<TEAM>();
     T k_next = T(0);
     bool ok = true;
     for (int t = a.N - 1; t >= 0; --t) {
-        for (int e = lane; e < nn; e += 32) Fz[e] = a.F_z[a.lFz.at(b, t, e)];
-        for (int e = lane; e < nz; e += 32) Fu[e] = a.F_u[a.lFu.at(b, t, e)];
-        __syncwarp();
+        for (int e = lane; e < nn; e += TEAM) Fz[e] = a.F_z[a.lFz.at(b, t, e)];
+        for (int e = lane; e < nz; e += TEAM) Fu[e] = a.F_u[a.lFu.at(b, t, e)];
+        team_sync<TEAM>();
         // W = V Fz ; wu = V Fu
-        for (int e = lane; e < nn; e += 32) {
+        for (int e = lane; e < nn; e += TEAM) {
             const int i = e / nz, j = e - i * nz;
             T s = T(0);
             for (int kk = 0; kk < nz; ++kk) s += V[i * nz + kk] * Fz[kk * nz + j];
             W[e] = s;
         }
-        for (int i = lane; i < nz; i += 32) {
+        for (int i = lane; i < nz; i += TEAM) {
             T s = T(0);
             for (int kk = 0; kk < nz; ++kk) s += V[i * nz + kk] * Fu[kk];
             wu[i] = s;
         }
-        __syncwarp();
+        team_sync<TEAM>();
         // Q_z, Q_uz (vectors), Q_u, Q_uu (scalars, every lane computes them redundantly)
-        for (int i = lane; i < nz; i += 32) {
+        for (int i = lane; i < nz; i += TEAM) {
             T sz = a.L_z[a.lLz.at(b, t, i)], suz = a.L_uz[a.lLuz.at(b, t, i)];
             for (int kk = 0; kk < nz; ++kk) {
                 sz += Fz[kk * nz + i] * v[kk];
@@ -262,9 +274,9 @@ __global__ void __launch_bounds__(128) backward_warp_kernel(const BackwardArgs<T
             Qu += Fu[kk] * v[kk];
             Quu += Fu[kk] * wu[kk];
         }
-        __syncwarp();
+        team_sync<TEAM>();
         // Q_zz = L_zz + Fz^T W  -> overwrites V (V is dead once W and wu exist)
-        for (int e = lane; e < nn; e += 32) {
+        for (int e = lane; e < nn; e += TEAM) {
             const int i = e / nz, j = e - i * nz;
             T s = a.L_zz[a.lLzz.at(b, t, e)];
             for (int kk = 0; kk < nz; ++kk) s += Fz[kk * nz + i] * W[kk * nz + j];
@@ -274,22 +286,22 @@ __global__ void __launch_bounds__(128) backward_warp_kernel(const BackwardArgs<T
         T ut = bounded ? a.U[a.lU.at(b, t, 0)] : T(0);
         ok = gains1(Quu, Qu, reg, bounded, lo - ut, hi - ut, k_next, kt, inv);
         bool bad = false;
-        for (int i = lane; i < nz; i += 32) {
+        for (int i = lane; i < nz; i += TEAM) {
             T Ki = -Quz[i] * inv;
             Kt[i] = Ki;
             bad |= (Ki != Ki);
         }
-        ok = ok && !__any_sync(0xffffffffu, bad);
+        ok = ok && !team_any<TEAM>(bad);
         if (!ok) break;
-        __syncwarp();
+        team_sync<TEAM>();
         k_next = kt;
         if (lane == 0) a.k[a.lk.at(b, t, 0)] = kt;
-        for (int i = lane; i < nz; i += 32) {
+        for (int i = lane; i < nz; i += TEAM) {
             a.K[a.lK.at(b, t, i)] = Kt[i];
             v[i] = Qz[i] + Kt[i] * Qu + Kt[i] * Quu * kt + Quz[i] * kt;
         }
         // symmetrise Q_zz and add the gain terms, one lane owns both (i,j) and (j,i)
-        for (int e = lane; e < nn; e += 32) {
+        for (int e = lane; e < nn; e += TEAM) {
             const int i = e / nz, j = e - i * nz;
             if (j < i) continue;
             T q = T(0.5) * (V[i * nz + j] + V[j * nz + i]);
@@ -297,7 +309,7 @@ __global__ void __launch_bounds__(128) backward_warp_kernel(const BackwardArgs<T
             V[i * nz + j] = val;
             V[j * nz + i] = val;
         }
-        __syncwarp();
+        team_sync<TEAM>();
     }
     if (lane == 0) a.status[b] = ok ? 0 : 1;
 }
@@ -311,14 +323,20 @@ cudaError_t backward_pass(const BackwardArgs<T>& a, int layout, cudaStream_t s) 
         else backward_thread_kernel<T, 4><<<grid, threads, 0, s>>>(a);
         return cudaGetLastError();
     }
-    const size_t per_warp = (size_t)(3 * a.nz * a.nz + 6 * a.nz) * sizeof(T);
+    const size_t per_team = (size_t)(3 * a.nz * a.nz + 6 * a.nz) * sizeof(T);
+    if (a.nz >= 24) {                                   // a CTA per problem
+        if (per_team > 227 * 1024) return cudaErrorInvalidValue;
+        cudaError_t e = cudaFuncSetAttribute(backward_warp_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_team);
+        if (e != cudaSuccess) return e;
+        backward_warp_kernel<T, 256><<<a.B, 256, per_team, s>>>(a);
+        return cudaGetLastError();
+    }
     int wpb = 4;
-    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
-    if (per_warp * wpb > 227 * 1024) return cudaErrorInvalidValue;
-    const size_t smem = per_warp * wpb;
-    cudaError_t e = cudaFuncSetAttribute(backward_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    while (wpb > 1 && per_team * wpb > 200 * 1024) wpb >>= 1;
+    const size_t smem = per_team * wpb;
+    cudaError_t e = cudaFuncSetAttribute(backward_warp_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    backward_warp_kernel<T><<<(a.B + wpb - 1) / wpb, wpb * 32, smem, s>>>(a);
+    backward_warp_kernel<T, 32><<<(a.B + wpb - 1) / wpb, wpb * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
 template cudaError_t backward_pass<float>(const BackwardArgs<float>&, int, cudaStream_t);

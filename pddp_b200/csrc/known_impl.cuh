@@ -193,11 +193,16 @@ __device__ __forceinline__ T roll_one(const RollKnownArgs<T>& a, int b, T alpha,
     return J;
 }
 
+// GA lanes = the alphas of one problem, 32/GA problems per warp (GA = 10: three problems on 30 lanes,
+// the reference's default line search has 10 alphas; GA = 16 / 32 for longer searches).
 template <class T, int GEO, int ENC, int GA>
 __global__ void __launch_bounds__(128) rollout_known_kernel(const RollKnownArgs<T> a) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = tid / GA, lane = tid % GA;
-    const bool live = b < a.B && (!a.active || a.active[b] != 0) && (!a.bw_status || a.bw_status[b] == 0);
+    constexpr int GPW = 32 / GA;                           // problems per warp
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int lane32 = threadIdx.x & 31, grp = lane32 / GA, lane = lane32 - grp * GA;
+    const int64_t b64 = (tid >> 5) * GPW + grp;
+    const int b = (int)b64;
+    const bool live = grp < GPW && b64 < a.B && (!a.active || a.active[b] != 0) && (!a.bw_status || a.bw_status[b] == 0);
     const bool bounded = a.u_min != nullptr && a.u_max != nullptr;
     T lo = bounded ? a.u_min[0] : T(0), hi = bounded ? a.u_max[0] : T(0);
     const bool has_alpha = live && lane < a.A;
@@ -205,21 +210,20 @@ __global__ void __launch_bounds__(128) rollout_known_kernel(const RollKnownArgs<
     T J = has_alpha ? roll_one<T, GEO, ENC, false>(a, b, alpha, bounded, lo, hi) : T(INFINITY);
     if (has_alpha) a.J_all[(int64_t)b * a.A + lane] = J;
 
-    // argmin with torch semantics: NaN beats everything, ties -> lowest index
+    // argmin with torch semantics (NaN beats everything, ties -> lowest index): every lane scans
+    // its group's candidates in index order
     const unsigned full = 0xffffffffu;
-    T best = J;
-    int idx = has_alpha ? lane : GA;
-    bool nan = has_alpha && (J != J);
+    T best = T(INFINITY);
+    int idx = 0;
+    bool nan = false, any = false;
 #pragma unroll
-    for (int off = GA / 2; off > 0; off >>= 1) {
-        T oJ = __shfl_xor_sync(full, best, off, GA);
-        int oi = __shfl_xor_sync(full, idx, off, GA);
-        bool on = __shfl_xor_sync(full, (int)nan, off, GA) != 0;
-        bool take;
-        if (nan != on) take = on;
-        else if (nan) take = oi < idx;
-        else take = (oJ < best) || (oJ == best && oi < idx);
-        if (take) { best = oJ; idx = oi; nan = on; }
+    for (int c = 0; c < GA; ++c) {
+        const int src = (grp < GPW ? grp : 0) * GA + c;
+        const T oJ = __shfl_sync(full, J, src);
+        if (c >= a.A) continue;
+        const bool on = oJ != oJ;
+        const bool take = !any || (!nan && (on || oJ < best));
+        if (take) { best = oJ; idx = c; nan = on; any = true; }
     }
     if (!live) return;
     if (lane == 0) {
@@ -254,11 +258,14 @@ static cudaError_t launch_lin(const LinKnownArgs<T>& a, cudaStream_t s) {
 template <class T, int GEO, int ENC>
 static cudaError_t launch_roll(const RollKnownArgs<T>& a, cudaStream_t s) {
     const int threads = 128;
-    if (a.A <= 16) {
-        int64_t total = (int64_t)a.B * 16;
+    if (a.A <= 10) {
+        const int64_t total = ((int64_t)a.B + 2) / 3 * 32;
+        rollout_known_kernel<T, GEO, ENC, 10><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(a);
+    } else if (a.A <= 16) {
+        const int64_t total = (int64_t)a.B * 16;
         rollout_known_kernel<T, GEO, ENC, 16><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(a);
     } else {
-        int64_t total = (int64_t)a.B * 32;
+        const int64_t total = (int64_t)a.B * 32;
         rollout_known_kernel<T, GEO, ENC, 32><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(a);
     }
     rollout_known_store_kernel<T, GEO, ENC><<<(a.B + threads - 1) / threads, threads, 0, s>>>(a);

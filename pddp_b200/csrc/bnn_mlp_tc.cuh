@@ -33,6 +33,7 @@
 #pragma once
 #include "bnn_mlp_simt.cuh"
 #include <cuda_fp16.h>
+#include <type_traits>
 
 namespace pddp {
 namespace tc {
@@ -183,8 +184,12 @@ __device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, float* v) {
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
-#pragma unroll
-    for (int e = 8; e < 16; ++e) r[e] = 0;
+}
+__device__ __forceinline__ void tc_wait_ld8(float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :: "memory");
 }
 // tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled
 // above the wait.
@@ -672,54 +677,62 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     for (int o = 0; o < D; ++o) y[jr][o] = 0.f;
                 mbar_wait(&acc1_full[t], (uint32_t)k & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int c0 = 0; c0 < TILE_N; c0 += 32) {
-                    constexpr int NG_MAX = 4;                                   // 8-column groups per batch
-                    const int ng = (TILE_N - c0) / 8 < NG_MAX ? (TILE_N - c0) / 8 : NG_MAX;
-                    float f[2][4 * NG_MAX];
+                // 6 batches of 32 columns + one of 16, as a ROLLED loop (a fully unrolled epilogue is 1 400 SASS
+                // instructions; with five roles resident the instruction cache misses showed up as 26 % of the
+                // epilogue's stall samples).  TAN: one gate word per batch, kept in a 7-register queue that is
+                // pushed (primal pass) or rotated (tangent passes) once per batch -- no dynamic register index.
+                auto batch = [&](const int c0, auto ng_tag) {
+                    constexpr int NG = decltype(ng_tag)::value;                 // 8-column groups in this batch
+                    float f[2][4 * NG];
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         const uint32_t ta = track_taddr + ((uint32_t)(w * 32 + hf * 16) << 16) + TM_ACC1 + c0;
-                        if (ng == 4) tc_ld_16x256b_x4(ta, f[hf]);
+                        if (NG == 4) tc_ld_16x256b_x4(ta, f[hf]);
                         else tc_ld_16x256b_x2(ta, f[hf]);
                     }
-                    tc_wait_ld16(f[0]);
-                    tc_wait_ld16(f[1]);
+                    if (NG == 4) { tc_wait_ld16(f[0]); tc_wait_ld16(f[1]); }
+                    else { tc_wait_ld8(f[0]); tc_wait_ld8(f[1]); }
+                    uint32_t word = TAN ? gate[6] : 0u;                         // tangent passes: this batch's gates
+                    if (TAN && d == 0) word = 0u;
 #pragma unroll
-                    for (int gi = 0; gi < NG_MAX; ++gi) {
-                        if (gi < ng) {
-                            float w2[2][DP];                                    // output weights of this thread's 2 columns
+                    for (int gi = 0; gi < NG; ++gi) {
+                        float w2[2][DP];                                        // output weights of this thread's 2 columns
 #pragma unroll
-                            for (int cc = 0; cc < 2; ++cc)
+                        for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
-                                for (int o4 = 0; o4 < DP / 4; ++o4)
-                                    *reinterpret_cast<float4*>(&w2[cc][4 * o4]) =
-                                        lds128f(W2s + (uint32_t)(((c0 + 8 * gi + 2 * q4 + cc) * DP + 4 * o4) * 4));
+                            for (int o4 = 0; o4 < DP / 4; ++o4)
+                                *reinterpret_cast<float4*>(&w2[cc][4 * o4]) =
+                                    lds128f(W2s + (uint32_t)(((c0 + 8 * gi + 2 * q4 + cc) * DP + 4 * o4) * 4));
 #pragma unroll
-                            for (int hf = 0; hf < 2; ++hf)
+                        for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-                                for (int hb = 0; hb < 2; ++hb)
+                            for (int hb = 0; hb < 2; ++hb)
 #pragma unroll
-                                    for (int cc = 0; cc < 2; ++cc) {
-                                        float vv = f[hf][4 * gi + 2 * hb + cc];
-                                        // element index of this value inside the thread's 208: fixed at compile time
-                                        const int eidx = ((c0 / 8 + gi) * 2 + hf) * 4 + 2 * hb + cc;
-                                        if (!TAN) {
-                                            vv = fmaxf(vv, 0.f);
-                                        } else if (d == 0) {
-                                            gate[eidx >> 5] = __funnelshift_l(__float_as_uint(vv), gate[eidx >> 5], 1);
-                                            vv = fmaxf(vv, 0.f);
-                                        } else {
-                                            // the sign was shifted in at position eidx%32 of its word: it sits at bit (n_w - 1 - eidx%32)
-                                            const int nw = (eidx >> 5) < 6 ? 32 : 16;
-                                            vv = (gate[eidx >> 5] & (1u << (nw - 1 - (eidx & 31)))) ? 0.f : vv;
-                                        }
-#pragma unroll
-                                        for (int o = 0; o < D; ++o) y[2 * hf + hb][o] += vv * w2[cc][o];
+                                for (int cc = 0; cc < 2; ++cc) {
+                                    float vv = f[hf][4 * gi + 2 * hb + cc];
+                                    constexpr int NE = 8 * NG;                   // elements of this thread in the batch
+                                    const int e = (gi * 2 + hf) * 4 + 2 * hb + cc;
+                                    if (!TAN) {
+                                        vv = fmaxf(vv, 0.f);
+                                    } else if (d == 0) {
+                                        word = __funnelshift_l(__float_as_uint(vv), word, 1);   // element e ends at bit NE-1-e
+                                        vv = fmaxf(vv, 0.f);
+                                    } else {
+                                        vv = (word & (1u << (NE - 1 - e))) ? 0.f : vv;
                                     }
-                        }
+#pragma unroll
+                                    for (int o = 0; o < D; ++o) y[2 * hf + hb][o] += vv * w2[cc][o];
+                                }
                     }
-                }
+                    if (TAN) {          // primal pass: push the new word; tangent passes: rotate (oldest = next batch)
+#pragma unroll
+                        for (int j = 6; j > 0; --j) gate[j] = gate[j - 1];
+                        gate[0] = word;
+                    }
+                };
+#pragma unroll 1
+                for (int c0 = 0; c0 < (TILE_N / 32) * 32; c0 += 32) batch(c0, std::integral_constant<int, 4>());
+                batch((TILE_N / 32) * 32, std::integral_constant<int, (TILE_N % 32) / 8>());
                 tc_fence_before();
                 mbar_arrive(&acc1_empty[t]);
                 // complete the column sums across the quad, then lane q4 writes outputs o = q4 (and q4 + 4)

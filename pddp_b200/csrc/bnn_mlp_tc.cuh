@@ -677,25 +677,12 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     for (int o = 0; o < D; ++o) y[jr][o] = 0.f;
                 mbar_wait(&acc1_full[t], (uint32_t)k & 1);
                 tc_fence_after();
-                // 6 batches of 32 columns + one of 16, as a ROLLED loop (a fully unrolled epilogue is 1 400 SASS
-                // instructions; with five roles resident the instruction cache misses showed up as 26 % of the
-                // epilogue's stall samples).  TAN: one gate word per batch, kept in a 7-register queue that is
-                // pushed (primal pass) or rotated (tangent passes) once per batch -- no dynamic register index.
-                auto batch = [&](const int c0, auto ng_tag) {
-                    constexpr int NG = decltype(ng_tag)::value;                 // 8-column groups in this batch
-                    float f[2][4 * NG];
+                // half = 16 columns (two 8-column groups) of both row halves; consumes fragment buffer fb and
+                // shifts / tests bits [ebase, ebase+16) of the current gate word
+                auto half = [&](const int c0, float (&fb)[2][8], uint32_t& word, auto ebase_tag, auto ne_tag) {
+                    constexpr int EBASE = decltype(ebase_tag)::value, NE = decltype(ne_tag)::value;
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const uint32_t ta = track_taddr + ((uint32_t)(w * 32 + hf * 16) << 16) + TM_ACC1 + c0;
-                        if (NG == 4) tc_ld_16x256b_x4(ta, f[hf]);
-                        else tc_ld_16x256b_x2(ta, f[hf]);
-                    }
-                    if (NG == 4) { tc_wait_ld16(f[0]); tc_wait_ld16(f[1]); }
-                    else { tc_wait_ld8(f[0]); tc_wait_ld8(f[1]); }
-                    uint32_t word = TAN ? gate[6] : 0u;                         // tangent passes: this batch's gates
-                    if (TAN && d == 0) word = 0u;
-#pragma unroll
-                    for (int gi = 0; gi < NG; ++gi) {
+                    for (int gi = 0; gi < 2; ++gi) {
                         float w2[2][DP];                                        // output weights of this thread's 2 columns
 #pragma unroll
                         for (int cc = 0; cc < 2; ++cc)
@@ -709,9 +696,8 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                             for (int hb = 0; hb < 2; ++hb)
 #pragma unroll
                                 for (int cc = 0; cc < 2; ++cc) {
-                                    float vv = f[hf][4 * gi + 2 * hb + cc];
-                                    constexpr int NE = 8 * NG;                   // elements of this thread in the batch
-                                    const int e = (gi * 2 + hf) * 4 + 2 * hb + cc;
+                                    float vv = fb[hf][4 * gi + 2 * hb + cc];
+                                    const int e = EBASE + (gi * 2 + hf) * 4 + 2 * hb + cc;
                                     if (!TAN) {
                                         vv = fmaxf(vv, 0.f);
                                     } else if (d == 0) {
@@ -724,15 +710,41 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                                     for (int o = 0; o < D; ++o) y[2 * hf + hb][o] += vv * w2[cc][o];
                                 }
                     }
-                    if (TAN) {          // primal pass: push the new word; tangent passes: rotate (oldest = next batch)
-#pragma unroll
-                        for (int j = 6; j > 0; --j) gate[j] = gate[j - 1];
-                        gate[0] = word;
-                    }
                 };
+                auto issue = [&](const int c0, float (&fb)[2][8]) {
+                    const uint32_t ta = track_taddr + ((uint32_t)(w * 32) << 16) + TM_ACC1 + c0;
+                    tc_ld_16x256b_x2(ta, fb[0]);
+                    tc_ld_16x256b_x2(ta + (16u << 16), fb[1]);
+                };
+                auto push = [&](uint32_t word) {   // primal pass: push the new word; tangent passes: rotate (oldest = next)
+#pragma unroll
+                    for (int j = 6; j > 0; --j) gate[j] = gate[j - 1];
+                    gate[0] = word;
+                };
+                // 13 sixteen-column batches, two per trip of a ROLLED loop (a fully unrolled epilogue is 1 400 SASS
+                // instructions: with five roles resident, instruction-cache misses were 26 % of its stall samples),
+                // software pipelined over two fragment buffers: the TMEM loads of the next batch are issued right
+                // after the wait for the current one (tcgen05.wait::ld waits for everything outstanding).
+                float fa[2][8], fb2[2][8];
+                issue(0, fa);
 #pragma unroll 1
-                for (int c0 = 0; c0 < (TILE_N / 32) * 32; c0 += 32) batch(c0, std::integral_constant<int, 4>());
-                batch((TILE_N / 32) * 32, std::integral_constant<int, (TILE_N % 32) / 8>());
+                for (int c0 = 0; c0 < (TILE_N / 32) * 32; c0 += 32) {
+                    uint32_t word = (TAN && d != 0) ? gate[6] : 0u;
+                    tc_wait_ld8(fa[0]); tc_wait_ld8(fa[1]);
+                    issue(c0 + 16, fb2);
+                    half(c0, fa, word, std::integral_constant<int, 0>(), std::integral_constant<int, 32>());
+                    tc_wait_ld8(fb2[0]); tc_wait_ld8(fb2[1]);
+                    issue(c0 + 32, fa);
+                    half(c0 + 16, fb2, word, std::integral_constant<int, 16>(), std::integral_constant<int, 32>());
+                    if (TAN) push(word);
+                }
+                {
+                    static_assert(TILE_N % 32 == 16, "epilogue tail handles one 16-column batch");
+                    uint32_t word = (TAN && d != 0) ? gate[6] : 0u;
+                    tc_wait_ld8(fa[0]); tc_wait_ld8(fa[1]);
+                    half((TILE_N / 32) * 32, fa, word, std::integral_constant<int, 0>(), std::integral_constant<int, 16>());
+                    if (TAN) push(word);
+                }
                 tc_fence_before();
                 mbar_arrive(&acc1_empty[t]);
                 // complete the column sums across the quad, then lane q4 writes outputs o = q4 (and q4 + 4)

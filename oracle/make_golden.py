@@ -229,6 +229,14 @@ def main():
                    E.FULL_COVARIANCE_MATRIX, f64, 4, 25, bnn=([32, 32], 16, 0.05))
     ok &= run_case("bnn_double_cartpole_full_f64", "double_cartpole", E.FULL_COVARIANCE_MATRIX, f64,
                    3, 26, bnn=([200, 200], 50, 0.02))
+    # the two diagonal encodings
+    for name in PROBLEMS:
+        for enc, etag in ((E.VARIANCE_ONLY, "var"), (E.STANDARD_DEVIATION_ONLY, "std")):
+            ok &= run_case("known_%s_%s_f64" % (name, etag), name, enc, f64, 12, 11)
+    ok &= run_case("bnn_cartpole_var_small_f64", "cartpole", E.VARIANCE_ONLY, f64, 5, 31,
+                   bnn=([32, 32], 12, 0.05))
+    ok &= run_case("bnn_cartpole_std_small_f64", "cartpole", E.STANDARD_DEVIATION_ONLY, f64, 5, 32,
+                   bnn=([32, 32], 12, 0.05))
     print("ALL OK" if ok else "SOME MISMATCH")
     return 0 if ok else 1
 

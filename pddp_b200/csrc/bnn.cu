@@ -172,6 +172,12 @@ __global__ void __launch_bounds__(128) bnn_moment_lin_kernel(const MomentLinArgs
                     for (int c = 0; c < D; ++c)
                         S[r][c] = ((r == ja && c == jb) ? T(0.5) : T(0)) + ((r == jb && c == ja) ? T(0.5) : T(0));
                 chol_upper_diff<D, T>(U, S, dUd);
+            } else if (ENC == ENC_VAR) {         // U = diag(sqrt(v)): dU_aa / dv_a = 1 / (2 U_aa)
+#pragma unroll
+                for (int r = 0; r < D; ++r) dUd[r][r] = (j - D == r) ? T(0.5) / U[r][r] : T(0);
+            } else if (ENC == ENC_STD) {
+#pragma unroll
+                for (int r = 0; r < D; ++r) dUd[r][r] = (j - D == r) ? T(1) : T(0);
             }
         }
         T dM[D], S2[D][D];
@@ -221,6 +227,9 @@ __global__ void __launch_bounds__(128) bnn_moment_lin_kernel(const MomentLinArgs
                 for (int r = 0; r < D; ++r)
 #pragma unroll
                     for (int c = 0; c < D; ++c) col[D + r * D + c] = dC[r][c];
+            } else if (ENC == ENC_VAR || ENC == ENC_STD) {      // var' = diag(C'), std' = sqrt(diag(C'))
+#pragma unroll
+                for (int r = 0; r < D; ++r) col[D + r] = ENC == ENC_VAR ? dC[r][r] : dC[r][r] / (T(2) * zn[D + r]);
             } else {
                 T dUn[D][D];
                 chol_upper_diff<D, T>(Un, dC, dUn);
@@ -644,6 +653,12 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
         case GEO_PENDULUM * 8 + ENC_FULL: return IMPL<T, GEO_PENDULUM, ENC_FULL>(call);                   \
         case GEO_PENDULUM * 8 + ENC_UT: return IMPL<T, GEO_PENDULUM, ENC_UT>(call);                       \
         case GEO_PENDULUM * 8 + ENC_IGNORE: return IMPL<T, GEO_PENDULUM, ENC_IGNORE>(call);               \
+        case GEO_PENDULUM * 8 + ENC_VAR: return IMPL<T, GEO_PENDULUM, ENC_VAR>(call);                     \
+        case GEO_PENDULUM * 8 + ENC_STD: return IMPL<T, GEO_PENDULUM, ENC_STD>(call);                     \
+        case GEO_CARTPOLE * 8 + ENC_VAR: return IMPL<T, GEO_CARTPOLE, ENC_VAR>(call);                     \
+        case GEO_CARTPOLE * 8 + ENC_STD: return IMPL<T, GEO_CARTPOLE, ENC_STD>(call);                     \
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_VAR: return IMPL<T, GEO_DOUBLE_CARTPOLE, ENC_VAR>(call);       \
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_STD: return IMPL<T, GEO_DOUBLE_CARTPOLE, ENC_STD>(call);       \
         case GEO_CARTPOLE * 8 + ENC_FULL: return IMPL<T, GEO_CARTPOLE, ENC_FULL>(call);                   \
         case GEO_CARTPOLE * 8 + ENC_UT: return IMPL<T, GEO_CARTPOLE, ENC_UT>(call);                       \
         case GEO_CARTPOLE * 8 + ENC_IGNORE: return IMPL<T, GEO_CARTPOLE, ENC_IGNORE>(call);               \
@@ -666,8 +681,6 @@ int pddp_capi_check_shape(const pddp_shape* s);         // capi.cu
 
 static int check_bnn(const pddp_shape* s, const pddp_bnn* n) {
     if (int e = pddp_capi_check_shape(s)) return e;
-    if (s->enc == PDDP_ENC_VARIANCE_ONLY || s->enc == PDDP_ENC_STANDARD_DEVIATION_ONLY)
-        return pddp_capi_fail(PDDP_E_UNSUPPORTED, "BNN: VARIANCE_ONLY / STANDARD_DEVIATION_ONLY not built (SURVEY 8f)");
     if (s->layout != PDDP_PROBLEM_MAJOR) return pddp_capi_fail(PDDP_E_UNSUPPORTED, "BNN path uses PDDP_PROBLEM_MAJOR");
     if (!n) return pddp_capi_fail(PDDP_E_BADARG, "bnn is NULL");
     if (n->P < 2 || n->P > 1024) return pddp_capi_fail(PDDP_E_BADARG, "2 <= particles <= 1024");

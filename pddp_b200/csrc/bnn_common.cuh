@@ -113,6 +113,8 @@ __device__ __forceinline__ bool load_factor(const T* z, T (&U)[D][D]) {
 #pragma unroll
         for (int b = 0; b < D; ++b) {
             if (ENC == ENC_UT) U[a][b] = b >= a ? z[D + tri<D>(a, b)] : T(0);
+            else if (ENC == ENC_VAR) U[a][b] = a == b ? jsqrt(z[D + a]) : T(0);      // diag(var).sqrt()
+            else if (ENC == ENC_STD) U[a][b] = a == b ? z[D + a] : T(0);             // diag(std)
             else U[a][b] = a == b ? T(1e-3) : T(0);
         }
     return true;
@@ -137,6 +139,10 @@ __device__ __forceinline__ bool encode_moments(const T* M, const T (&Cov)[D][D],
 #pragma unroll
             for (int b = a; b < D; ++b) zn[D + tri<D>(a, b)] = Un[a][b];
         return ok;
+    }
+    if (ENC == ENC_VAR || ENC == ENC_STD) {      // ref: encoding.py:131-134 (_V_from / _S_from of C)
+#pragma unroll
+        for (int a = 0; a < D; ++a) zn[D + a] = ENC == ENC_VAR ? Cov[a][a] : jsqrt(Cov[a][a]);
     }
     return true;
 }

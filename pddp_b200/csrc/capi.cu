@@ -92,8 +92,6 @@ extern "C" int pddp_linearize_known(const pddp_shape* s, const pddp_known_dynami
                                     void* L_u, void* L_zz, void* L_uz, void* L_uu, void* J_opt,
                                     int32_t* status, void* stream) {
     if (int e = check_shape(s)) return e;
-    if (s->enc == PDDP_ENC_VARIANCE_ONLY || s->enc == PDDP_ENC_STANDARD_DEVIATION_ONLY)
-        return fail(PDDP_E_UNSUPPORTED, "VARIANCE_ONLY / STANDARD_DEVIATION_ONLY not built (SURVEY 8f)");
     if (!dyn || !cost || !z0 || !U || !Z || !F_z || !F_u || !L || !L_z || !L_u || !L_zz || !L_uz || !L_uu || !J_opt)
         return fail(PDDP_E_BADARG, "pddp_linearize_known: NULL argument");
     if ((u_min == nullptr) != (u_max == nullptr)) return fail(PDDP_E_BADARG, "u_min and u_max must be given together");
@@ -169,8 +167,6 @@ extern "C" int pddp_rollout_known(const pddp_shape* s, const pddp_known_dynamics
     if (int e = check_shape(s)) return e;
     if (!dyn || !cost || !Z || !U || !k || !K || !alphas || !J_all || !amin || !J_new || !Z_new || !U_new)
         return fail(PDDP_E_BADARG, "pddp_rollout_known: NULL argument");
-    if (s->enc == PDDP_ENC_VARIANCE_ONLY || s->enc == PDDP_ENC_STANDARD_DEVIATION_ONLY)
-        return fail(PDDP_E_UNSUPPORTED, "VARIANCE_ONLY / STANDARD_DEVIATION_ONLY not built (SURVEY 8f)");
     if (A < 1 || A > 32) return fail(PDDP_E_UNSUPPORTED, "1 <= A <= 32 line-search candidates");
     if ((u_min == nullptr) != (u_max == nullptr)) return fail(PDDP_E_BADARG, "u_min and u_max must be given together");
     cudaStream_t st = (cudaStream_t)stream;
@@ -234,8 +230,6 @@ extern "C" int pddp_cost_derivatives(const pddp_shape* s, const pddp_cost* cost,
                                      const int32_t* active, void* L, void* L_z, void* L_u, void* L_zz,
                                      void* L_uz, void* L_uu, void* J_opt, void* stream) {
     if (int e = check_shape(s)) return e;
-    if (s->enc == PDDP_ENC_VARIANCE_ONLY || s->enc == PDDP_ENC_STANDARD_DEVIATION_ONLY)
-        return fail(PDDP_E_UNSUPPORTED, "pddp_cost_derivatives: VARIANCE_ONLY / STANDARD_DEVIATION_ONLY not built (SURVEY 8f)");
     if (!cost || !Z || !U || !L || !L_z || !L_u || !L_zz || !L_uz || !L_uu)
         return fail(PDDP_E_BADARG, "pddp_cost_derivatives: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;

@@ -277,6 +277,12 @@ static cudaError_t launch_roll(const RollKnownArgs<T>& a, cudaStream_t s) {
         case GEO_PENDULUM * 8 + ENC_FULL: return FN<T, GEO_PENDULUM, ENC_FULL>(__VA_ARGS__);      \
         case GEO_PENDULUM * 8 + ENC_UT: return FN<T, GEO_PENDULUM, ENC_UT>(__VA_ARGS__);          \
         case GEO_PENDULUM * 8 + ENC_IGNORE: return FN<T, GEO_PENDULUM, ENC_IGNORE>(__VA_ARGS__);  \
+        case GEO_PENDULUM * 8 + ENC_VAR: return FN<T, GEO_PENDULUM, ENC_VAR>(__VA_ARGS__);        \
+        case GEO_PENDULUM * 8 + ENC_STD: return FN<T, GEO_PENDULUM, ENC_STD>(__VA_ARGS__);        \
+        case GEO_CARTPOLE * 8 + ENC_VAR: return FN<T, GEO_CARTPOLE, ENC_VAR>(__VA_ARGS__);        \
+        case GEO_CARTPOLE * 8 + ENC_STD: return FN<T, GEO_CARTPOLE, ENC_STD>(__VA_ARGS__);        \
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_VAR: return FN<T, GEO_DOUBLE_CARTPOLE, ENC_VAR>(__VA_ARGS__); \
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_STD: return FN<T, GEO_DOUBLE_CARTPOLE, ENC_STD>(__VA_ARGS__); \
         case GEO_CARTPOLE * 8 + ENC_FULL: return FN<T, GEO_CARTPOLE, ENC_FULL>(__VA_ARGS__);      \
         case GEO_CARTPOLE * 8 + ENC_UT: return FN<T, GEO_CARTPOLE, ENC_UT>(__VA_ARGS__);          \
         case GEO_CARTPOLE * 8 + ENC_IGNORE: return FN<T, GEO_CARTPOLE, ENC_IGNORE>(__VA_ARGS__);  \

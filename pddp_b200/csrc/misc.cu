@@ -160,6 +160,12 @@ cudaError_t cost_derivatives(int geo, int enc, const CostDerivArgs<T>& a, cudaSt
         case GEO_PENDULUM * 8 + ENC_FULL: return launch_cost<T, GEO_PENDULUM, ENC_FULL>(a, s);
         case GEO_PENDULUM * 8 + ENC_UT: return launch_cost<T, GEO_PENDULUM, ENC_UT>(a, s);
         case GEO_PENDULUM * 8 + ENC_IGNORE: return launch_cost<T, GEO_PENDULUM, ENC_IGNORE>(a, s);
+        case GEO_PENDULUM * 8 + ENC_VAR: return launch_cost<T, GEO_PENDULUM, ENC_VAR>(a, s);
+        case GEO_PENDULUM * 8 + ENC_STD: return launch_cost<T, GEO_PENDULUM, ENC_STD>(a, s);
+        case GEO_CARTPOLE * 8 + ENC_VAR: return launch_cost<T, GEO_CARTPOLE, ENC_VAR>(a, s);
+        case GEO_CARTPOLE * 8 + ENC_STD: return launch_cost<T, GEO_CARTPOLE, ENC_STD>(a, s);
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_VAR: return launch_cost<T, GEO_DOUBLE_CARTPOLE, ENC_VAR>(a, s);
+        case GEO_DOUBLE_CARTPOLE * 8 + ENC_STD: return launch_cost<T, GEO_DOUBLE_CARTPOLE, ENC_STD>(a, s);
         case GEO_CARTPOLE * 8 + ENC_FULL: return launch_cost<T, GEO_CARTPOLE, ENC_FULL>(a, s);
         case GEO_CARTPOLE * 8 + ENC_UT: return launch_cost<T, GEO_CARTPOLE, ENC_UT>(a, s);
         case GEO_CARTPOLE * 8 + ENC_IGNORE: return launch_cost<T, GEO_CARTPOLE, ENC_IGNORE>(a, s);

@@ -112,6 +112,13 @@ def test_loud_failures():
     with pytest.raises(RuntimeError):
         BatchedSolver(KnownDynamics(_lib.GEO_PENDULUM, [0.1, 1, 1, 0.1, 9.8]), cost, 4, 1, 5,
                       device="cpu")
-    s = BatchedSolver(KnownDynamics(_lib.GEO_PENDULUM, [0.1, 1, 1, 0.1, 9.8]), cost, 2, 1, 5)
-    with pytest.raises(RuntimeError, match="not built"):
+    # an unsupported configuration fails loudly through the C ABI's error code: hidden width > 256
+    from pddp_b200.solver import BNNDynamics
+    H, P = 300, 4
+    dyn = BNNDynamics(_lib.GEO_PENDULUM, [torch.zeros(H, 4), torch.zeros(H, H), torch.zeros(4, H)],
+                      [torch.zeros(H), torch.zeros(H), torch.zeros(4)], [torch.ones(P, H), torch.ones(P, H)],
+                      torch.zeros(P, 2))
+    with pytest.raises((RuntimeError, ValueError), match="hidden widths"):
+        s = BatchedSolver(dyn, cost, 4, 1, 5)
+        s.set_problem(torch.zeros(1, 2).cuda(), torch.zeros(1, 5, 1).cuda())
         s.linearize()

@@ -95,8 +95,51 @@ template cudaError_t accept_update<double>(const AcceptArgs<double>&, int32_t*, 
 // Stand-alone cost linearisation: one thread per (problem, time, Hessian pair).
 // Replaces batch_eval_cost (pddp/utils/evaluation.py:134-239) for a whole nominal trajectory.
 // ------------------------------------------------------------------------------------------
+// Pair order for FULL_COVARIANCE_MATRIX: the cost is LINEAR in most covariance entries (trace term and the
+// cross blocks of the augmented covariance, core.cuh cost_state), so most of the nz(nz+1)/2 Hessian pairs
+// are structurally zero.  c_pair_order lists the pairs that can be non-zero first -- every diagonal pair
+// (it also carries the gradient), pairs inside {means, C[ang][ang]}, and C[ang_i][*] / C[*][ang_i] against
+// {m_ang_i, C[ang_i][ang_i]} -- then the rest, which only get zeros written (double cartpole: 119 of 903
+// pairs are evaluated).  Entry = i * 256 + j.
+__constant__ uint16_t c_pair_order[3][1024];
+static int g_pair_nnz[3] = {-1, -1, -1};
+
+template <int GEO>
+static cudaError_t fill_pair_order(int* nnz_out) {
+    typedef Geo<GEO> G;
+    constexpr int D = G::D, NZ = D + D * D;
+    if (g_pair_nnz[GEO] >= 0) { *nnz_out = g_pair_nnz[GEO]; return cudaSuccess; }
+    auto is_ang = [](int a) { for (int i = 0; i < G::NANG; ++i) if (G::ang(i) == a) return true; return false; };
+    // class of a variable: 0 mean, 1 C[ang][ang], 2 C with exactly one angular index, 3 C[nonang][nonang]
+    auto cls = [&](int v, int& angle) {
+        angle = -1;
+        if (v < D) { if (is_ang(v)) angle = v; return 0; }
+        const int a = (v - D) / D, b = (v - D) % D;
+        if (is_ang(a) && is_ang(b)) { if (a == b) angle = a; return 1; }
+        if (is_ang(a) || is_ang(b)) { angle = is_ang(a) ? a : b; return 2; }
+        return 3;
+    };
+    uint16_t order[1024];
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int i = 0; i < NZ; ++i)
+            for (int j = i; j < NZ; ++j) {
+                int ai, aj;
+                const int ci = cls(i, ai), cj = cls(j, aj);
+                bool nonzero = i == j || (ci <= 1 && cj <= 1);
+                if (ci == 2 && cj <= 1 && aj == ai) nonzero = true;      // C[ang_i][.] x {m_ang_i, C[ang_i][ang_i]}
+                if (cj == 2 && ci <= 1 && ai == aj) nonzero = true;
+                if ((pass == 0) == nonzero) order[n++] = (uint16_t)(i * 256 + j);
+                if (pass == 0 && i == NZ - 1 && j == NZ - 1) g_pair_nnz[GEO] = n;
+            }
+    cudaError_t e = cudaMemcpyToSymbol(c_pair_order, order, sizeof(uint16_t) * n, sizeof(uint16_t) * 1024 * GEO);
+    if (e != cudaSuccess) { g_pair_nnz[GEO] = -1; return e; }
+    *nnz_out = g_pair_nnz[GEO];
+    return cudaSuccess;
+}
+
 template <class T, int GEO, int ENC>
-__global__ void __launch_bounds__(128) cost_pairs_kernel(const CostDerivArgs<T> a) {
+__global__ void __launch_bounds__(128) cost_pairs_kernel(const CostDerivArgs<T> a, int nnz) {
     typedef Geo<GEO> G;
     constexpr int D = G::D, NZ = enc_size(D, ENC), NP = NZ * (NZ + 1) / 2;
     const int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -105,9 +148,22 @@ __global__ void __launch_bounds__(128) cost_pairs_kernel(const CostDerivArgs<T> 
     int p = (int)(id - site * NP);
     const int b = (int)(site / (a.N + 1)), t = (int)(site - (int64_t)b * (a.N + 1));
     if (a.active && a.active[b] != 1) return;
-    int i = 0;
-    while (p >= NZ - i) { p -= NZ - i; ++i; }
-    const int j = i + p;
+    int i = 0, j;
+    const bool terminal = t == a.N;
+    if (ENC == ENC_FULL) {
+        const int e = c_pair_order[GEO][p];
+        i = e >> 8;
+        j = e & 255;
+        if (p >= nnz) {                               // structurally zero pair (never a diagonal one)
+            a.L_zz[a.lLzz.at(b, t, i * NZ + j)] = T(0);
+            a.L_zz[a.lLzz.at(b, t, j * NZ + i)] = T(0);
+            if (i == 0 && a.L_uz && !terminal) a.L_uz[a.lLuz.at(b, t, j)] = T(0);
+            return;
+        }
+    } else {
+        while (p >= NZ - i) { p -= NZ - i; ++i; }
+        j = i + p;
+    }
     typedef Jet2<T, 2> S;
     S zj[NZ];
 #pragma unroll
@@ -116,7 +172,6 @@ __global__ void __launch_bounds__(128) cost_pairs_kernel(const CostDerivArgs<T> 
         zj[k].g[0] = k == i ? T(1) : T(0);
         zj[k].g[1] = k == j ? T(1) : T(0);
     }
-    const bool terminal = t == a.N;
     S r = cost_state<GEO, ENC, T, S>(a.cost, zj, terminal);
     a.L_zz[a.lLzz.at(b, t, i * NZ + j)] = r.h[1];
     if (i != j) a.L_zz[a.lLzz.at(b, t, j * NZ + i)] = r.h[1];
@@ -149,7 +204,12 @@ template <class T, int GEO, int ENC>
 static cudaError_t launch_cost(const CostDerivArgs<T>& a, cudaStream_t s) {
     constexpr int NZ = enc_size(Geo<GEO>::D, ENC), NP = NZ * (NZ + 1) / 2;
     const int64_t total = (int64_t)a.B * (a.N + 1) * NP;
-    cost_pairs_kernel<T, GEO, ENC><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a);
+    int nnz = NP;
+    if (ENC == ENC_FULL) {
+        cudaError_t e = fill_pair_order<GEO>(&nnz);
+        if (e != cudaSuccess) return e;
+    }
+    cost_pairs_kernel<T, GEO, ENC><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a, nnz);
     if (a.J_opt) cost_sum_kernel<T><<<(a.B + 127) / 128, 128, 0, s>>>(a);
     return cudaGetLastError();
 }

@@ -212,6 +212,12 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -447,34 +453,46 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
     } else if (warp >= 16) {
         // ================= layer-1 issuers: one thread per track (a track that waits for its epilogue
         // or its mid-stage does not hold the other one up; they drift at most NB W1 stages apart) ====
-        if (lane == 0) {
-            const int t = warp - 16;
+        // The whole warp runs the loop with warp-uniform state (so the compiler keeps it in uniform
+        // registers and feeds UTCHMMA without per-operand R2UR / elect loops: the single-lane version
+        // spent ~1000 cycles of dependent scalar code per step for 318 cycles of MMA); one elected lane
+        // issues.  Descriptors advance by adding to their low word (address field, 16-byte units).
+        {
+            const int t = __shfl_sync(0xffffffffu, warp, 0) - 16;
+            const bool leader = elect_one();
+            const int ntiles = t == 0 ? ntl[0] : ntl[1], first_blk = t * skew;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC1);
+            const uint64_t desc_hi = make_desc<64>(0) & 0xFFFFFFFF00000000ull;
+            const uint32_t a_lo0 = (uint32_t)make_desc<64>(smem_u32(smem + C::A1_OFF + t * NS * A1_SLOT));
+            const uint32_t b_lo0 = (uint32_t)make_desc<64>(smem_u32(smem + C::B_OFF));
+            uint64_t* const a1f = a1_full + t * NS;
+            uint64_t* const a1e = a1_empty + t * NS;
             uint32_t s = 0, bph = 0, slot = 0, sph = 0;
-            int kb = 0, k = 0, pos = 0;
+            int k = 0, pos = 0;
             for (int nb = 0; nb < nblk; ++nb) {
                 mbar_wait(&b_full[s], bph);
-                if (nb < t * skew || k >= ntl[t]) {
-                    mbar_arrive(&b_empty[s]);               // this track does not use the block
+                if (nb < first_blk || k >= ntiles) {
+                    if (leader) mbar_arrive(&b_empty[s]);   // this track does not use the block
                 } else {
                     if (pos == 0) mbar_wait(&acc1_empty[t], ((uint32_t)k & 1) ^ 1);
-                    mbar_wait(&a1_full[t * NS + slot], sph);
+                    mbar_wait(&a1f[slot], sph);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC1);
-                    const uint32_t aa = smem_u32(smem + C::A1_OFF + (t * NS + slot) * A1_SLOT);
-                    const uint32_t bb = smem_u32(smem + C::B_OFF + s * B_STAGE);
-                    const uint64_t ad = make_desc<64>(aa), bd = make_desc<64>(bb);
-                    // one UMMA K-step = 32 B of a row = 16 fp16: [x0 | x1] halves are +2 apart in the >>4 address field
-                    tc_mma_f16(d_tmem, ad, bd, IDESC1, pos != 0);     // a0 * b0
-                    tc_mma_f16(d_tmem, ad, bd + 2, IDESC1, 1);        // a0 * b1
-                    tc_mma_f16(d_tmem, ad + 2, bd, IDESC1, 1);        // a1 * b0
-                    tc_commit(&a1_empty[t * NS + slot]);
-                    tc_commit(&b_empty[s]);
-                    if (pos == nkb - 1) tc_commit(&acc1_full[t]);
+                    if (leader) {
+                        const uint64_t ad = desc_hi | (uint64_t)(a_lo0 + slot * (A1_SLOT >> 4));
+                        const uint64_t bd = desc_hi | (uint64_t)(b_lo0 + s * (B_STAGE >> 4));
+                        // one UMMA K-step = 32 B of a row = 16 fp16: [x0 | x1] halves are +2 apart in the >>4 address field
+                        tc_mma_f16(d_tmem, ad, bd, IDESC1, pos != 0);     // a0 * b0
+                        tc_mma_f16(d_tmem, ad, bd + 2, IDESC1, 1);        // a0 * b1
+                        tc_mma_f16(d_tmem, ad + 2, bd, IDESC1, 1);        // a1 * b0
+                        tc_commit(&a1e[slot]);
+                        tc_commit(&b_empty[s]);
+                        if (pos == nkb - 1) tc_commit(&acc1_full[t]);
+                    }
+                    __syncwarp();
                     if (++slot == NS) { slot = 0; sph ^= 1; }
                     if (++pos == nkb) { pos = 0; ++k; }
                 }
                 if (++s == NB) { s = 0; bph ^= 1; }
-                if (++kb == nkb) kb = 0;
             }
         }
     } else {

@@ -146,8 +146,14 @@ __global__ void __launch_bounds__(128) bnn_moment_lin_kernel(const MomentLinArgs
         if ((e & 31) == lane) a.Z[a.lZ.at(b, t + 1, e)] = zn[e];
     if (lane == 0 && !ok && a.status) a.status[b] |= 2;
 
-    // one lane per input direction j in [z (NZ), u (NU)]
-    for (int j = lane; j < NZ + NU; j += 32) {
+    // SPLIT lanes per input direction j in [z (NZ), u (NU)], each taking every SPLIT-th particle (with
+    // one lane per direction only NZ + NU of the 32 lanes work: 15 for the UT-Cholesky cartpole)
+    constexpr int NJ = NZ + NU, SPLIT = NJ * 4 <= 32 ? 4 : (NJ * 2 <= 32 ? 2 : 1), JPW = 32 / SPLIT;
+    const int sub = lane % SPLIT;
+    for (int j0 = 0; j0 < NJ; j0 += JPW) {
+        const int jraw = j0 + lane / SPLIT;
+        const bool jvalid = jraw < NJ;
+        const int j = jvalid ? jraw : NJ - 1;
         T dm[D], dUd[D][D], du = T(0);
 #pragma unroll
         for (int d = 0; d < D; ++d) dm[d] = (j == d) ? T(1) : T(0);
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(128) bnn_moment_lin_kernel(const MomentLinArgs
 #pragma unroll
             for (int c = 0; c < D; ++c) S2[r][c] = T(0);
         }
-        for (int p = 0; p < P; ++p) {
+        for (int p = sub; p < P; p += SPLIT) {
             T dx[D], dxn[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) {
@@ -213,6 +219,20 @@ __global__ void __launch_bounds__(128) bnn_moment_lin_kernel(const MomentLinArgs
                     for (int c = 0; c < D; ++c) S2[r][c] += dxn[r] * s_xc[p * D + c];
             }
         }
+        if (SPLIT > 1) {
+#pragma unroll
+            for (int off = 1; off < SPLIT; off <<= 1) {
+#pragma unroll
+                for (int r = 0; r < D; ++r) {
+                    dM[r] += __shfl_xor_sync(0xffffffffu, dM[r], off);
+                    if (ENC != ENC_IGNORE) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) S2[r][c] += __shfl_xor_sync(0xffffffffu, S2[r][c], off);
+                    }
+                }
+            }
+        }
+        if (!jvalid || sub != 0) continue;
         T col[NZ];
 #pragma unroll
         for (int r = 0; r < D; ++r) col[r] = dM[r] / T(P);

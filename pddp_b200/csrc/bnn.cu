@@ -296,55 +296,82 @@ struct RollStepArgs {
     Layout lZ, lU, lk, lK;
 };
 
-// One THREAD per (problem, alpha): a warp-per-pair version left 31 lanes idle through the control
-// law and the cost (the moment-matched cost of an uncertain state is the long part) and spent most
-// of its issue slots on shuffles.  The 2 x P x D particle reads per thread are contiguous and L2
-// resident (the MLP kernel has just written them).
+// CTA = 256 threads = 32 (problem, alpha) pairs.  Phase A: 8 lanes per pair stream its P particles
+// (coalesced 128-byte rows of the [pair][particle][D] array) and reduce mean and covariance with
+// three xor-shuffles; phase B: warp 0, one lane per pair, does the encode (Cholesky), control law and
+// moment-matched cost.  (One thread per pair issued 2 x P strided 4-byte loads per sector and ran at
+// 9 % issue utilisation; a warp per pair left 31 lanes idle through phase B.)
 template <class T, int GEO, int ENC>
-__global__ void __launch_bounds__(64) bnn_roll_step_kernel(const RollStepArgs<T> a) {
+__global__ void __launch_bounds__(256) bnn_roll_step_kernel(const RollStepArgs<T> a) {
     typedef Geo<GEO> G;
-    constexpr int D = G::D, NZ = enc_size(D, ENC);
-    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (s >= (long long)a.B * a.A) return;
+    constexpr int D = G::D, NZ = enc_size(D, ENC), NT = D * (D + 1) / 2, LPP = 8, PPC = 32;
+    __shared__ T s_mom[PPC][D + NT];
+    const int tid = threadIdx.x;
+    const long long S = (long long)a.B * a.A;
+    const int P = a.P, t1 = a.t + 1;
+    if (a.t >= 0) {
+        const int pr = tid / LPP, sub = tid % LPP;
+        const long long s = (long long)blockIdx.x * PPC + pr;
+        const bool live = s < S;
+        const T* X = a.Xn + (size_t)(live ? s : 0) * P * D;
+        T M[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) M[d] = T(0);
+        if (live)
+            for (int p = sub; p < P; p += LPP)
+#pragma unroll
+                for (int d = 0; d < D; ++d) M[d] += X[p * D + d];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+#pragma unroll
+            for (int off = 1; off < LPP; off <<= 1) M[d] += __shfl_xor_sync(0xffffffffu, M[d], off);
+            M[d] /= T(P);
+        }
+        T cs[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) cs[i] = T(0);
+        if (live)
+            for (int p = sub; p < P; p += LPP) {
+                T xc[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) xc[d] = X[p * D + d] - M[d];
+#pragma unroll
+                for (int r = 0; r < D; ++r)
+#pragma unroll
+                    for (int c = r; c < D; ++c) cs[tri<D>(r, c)] += xc[r] * xc[c];
+            }
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+#pragma unroll
+            for (int off = 1; off < LPP; off <<= 1) cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], off);
+        }
+        if (sub == 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) s_mom[pr][d] = M[d];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) s_mom[pr][D + i] = cs[i] / T(P - 1);     // ref: utils/particles.py:136-149
+        }
+    }
+    __syncthreads();
+    if (tid >= PPC) return;
+    const long long s = (long long)blockIdx.x * PPC + tid;
+    if (s >= S) return;
     const int b = (int)(s / a.A), al = (int)(s - (long long)b * a.A);
     if ((a.active && a.active[b] == 0) || (a.bw_status && a.bw_status[b] != 0)) return;
-    const int P = a.P, t1 = a.t + 1;
     T zn[NZ];
     bool ok = true;
     if (a.t < 0) {
 #pragma unroll
         for (int e = 0; e < NZ; ++e) zn[e] = a.Z[a.lZ.at(b, 0, e)];
     } else {
-        const T* X = a.Xn + (size_t)s * P * D;
-        T M[D];
+        T M[D], Cov[D][D], Un[D][D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) M[d] = T(0);
-#pragma unroll 5
-        for (int p = 0; p < P; ++p)
-#pragma unroll
-            for (int d = 0; d < D; ++d) M[d] += X[p * D + d];
-#pragma unroll
-        for (int d = 0; d < D; ++d) M[d] /= T(P);
-        T Cov[D][D], Un[D][D];
-#pragma unroll
-        for (int r = 0; r < D; ++r)
-#pragma unroll
-            for (int c = 0; c < D; ++c) Cov[r][c] = T(0);
-#pragma unroll 5
-        for (int p = 0; p < P; ++p) {
-            T xc[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) xc[d] = X[p * D + d] - M[d];
-#pragma unroll
-            for (int r = 0; r < D; ++r)
-#pragma unroll
-                for (int c = r; c < D; ++c) Cov[r][c] += xc[r] * xc[c];
-        }
+        for (int d = 0; d < D; ++d) M[d] = s_mom[tid][d];
 #pragma unroll
         for (int r = 0; r < D; ++r)
 #pragma unroll
             for (int c = r; c < D; ++c) {
-                Cov[r][c] /= T(P - 1);
+                Cov[r][c] = s_mom[tid][D + tri<D>(r, c)];
                 Cov[c][r] = Cov[r][c];
             }
         ok = encode_moments<D, ENC, T>(M, Cov, zn, Un);
@@ -643,9 +670,9 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     r.lk = make_layout(ly, B, N, nu); r.lK = make_layout(ly, B, N, nu * nz);
     bnn_init_particles_kernel<T, GEO, ENC><<<(unsigned)((total + 127) / 128), 128, 0, c.st>>>(
         r.Z, r.lZ, A, S, P, net.eps0, w.Xa, c.status);
-    const unsigned rgrid = (unsigned)((S + 63) / 64);
+    const unsigned rgrid = (unsigned)((S + 31) / 32);
     r.t = -1; r.Xn = w.Xa;
-    bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 64, 0, c.st>>>(r);
+    bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 256, 0, c.st>>>(r);
     CK(cudaGetLastError());
     BnnMlpArgs<T> a;
     a.net = net; a.u = w.ucur; a.Jp = nullptr; a.total = total;
@@ -657,7 +684,7 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
         prof_end(PROF_MLP_ROLL, c.st);
         r.t = t; r.Xn = nxt;
         prof_begin(PROF_ROLL_STEP, c.st);
-        bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 64, 0, c.st>>>(r);
+        bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 256, 0, c.st>>>(r);
         prof_end(PROF_ROLL_STEP, c.st);
         T* tmp = cur; cur = nxt; nxt = tmp;
     }

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(128) bnn_moment_lin_kernel(const MomentLinArgs
     for (int j0 = 0; j0 < NJ; j0 += JPW) {
         const int jraw = j0 + lane / SPLIT;
         const bool jvalid = jraw < NJ;
+        if (SPLIT == 1 && !jvalid) continue;              // no shuffles below in that case
         const int j = jvalid ? jraw : NJ - 1;
         T dm[D], dUd[D][D], du = T(0);
 #pragma unroll

@@ -11,7 +11,7 @@
 //     (relu(m*x) = m*relu(x), m >= 0) and M1_p into a per-particle copy of the output weights --
 //     no mask is read in the inner loops;
 //   * layer 0 runs on the tensor core too: A0 = [norm(aug(X),u), 1] (K padded to 8/16) times the
-//     per-particle image, 3xTF32, 32 hidden units at a time into a small TMEM accumulator.  Row
+//     per-particle image, split FP16 like layer 1, 32 hidden units at a time into a small TMEM accumulator.  Row
 //     H0 of the image is the unit vector of the bias column, so hidden unit H0 is the constant 1
 //     that carries b1 through the second GEMM (b1 is column H0 of the W1 image);
 //   * layer 1 (the 200x200 contraction) runs in split FP16, a0*b0 + a0*b1 + a1*b0 with fp32
@@ -68,12 +68,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
-        "r"(accumulate) : "memory");
-}
 
 constexpr int TILE_M = 128, TILE_N = 208, KB = 16, MAX_NKB = 13, MAX_NCH = 7, N0 = 32;
 // Layer 1 in split FP16: a = a0 + a1, b = b0 + b1 with a0 = fp16(a), a1 = fp16(a - a0) (22
@@ -98,6 +92,12 @@ __host__ __device__ __forceinline__ uint32_t swz(int row, int kk) {
     const int chunk = (kk >> 2) ^ ((row & 7) >> SH);
     return (uint32_t)((row >> 3) * (8 * ROWB) + (row & 7) * ROWB + (chunk << 4) + (kk & 3) * 4);
 }
+// same, for a byte position inside the row
+template <int ROWB>
+__host__ __device__ __forceinline__ uint32_t swz_byte(int row, int byte) {
+    constexpr int SH = ROWB == 32 ? 2 : ROWB == 64 ? 1 : 0;
+    return (uint32_t)((row >> 3) * (8 * ROWB) + (row & 7) * ROWB + ((((byte >> 4) ^ ((row & 7) >> SH))) << 4) + (byte & 15));
+}
 // K-major shared-memory descriptor for rows of ROWB bytes (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) addr>>4, [16,30) LBO>>4 = 1, [32,46) SBO>>4 = 8 rows, [46,48) version 1, [61,64) layout type.
 template <int ROWB>
@@ -110,15 +110,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     d |= LT << 61;
     return d;
 }
-constexpr uint32_t idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
-// hi = x rounded to TF32 (round half away, like cvt.rna), lo = (x - hi) truncated to TF32
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-    lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
-}
 
 // two floats -> packed fp16x2 (a in the low half = lower address)
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
@@ -226,8 +218,8 @@ template <int K0P, int DP>
 struct Cfg {
     static constexpr int NB = K0P == 8 ? 5 : 4;    // W1 K-block stages
     static constexpr int NS = K0P == 8 ? 6 : 4;    // layer-1 A-operand slots per track
-    static constexpr int ROWB0 = K0P * 4;          // layer-0 operand row pitch (SWIZZLE_32B / 64B)
-    static constexpr int A0_PART = TILE_M * ROWB0, A0_BYTES = 2 * A0_PART;
+    static constexpr int ROWB0 = K0P * 4;          // layer-0 operand row [x0 (K0P fp16) | x1 (K0P fp16)]: SWIZZLE_32B / 64B
+    static constexpr int A0_BYTES = TILE_M * ROWB0;
     static constexpr int W0_CHUNK_PART = N0 * ROWB0, W0_CHUNK = 2 * W0_CHUNK_PART, W0_BYTES = MAX_NCH * W0_CHUNK;
     static constexpr int W2_BYTES = TILE_N * DP * 4;
     static constexpr int B_OFF = 0;
@@ -283,8 +275,10 @@ __global__ void prep_w1_kernel(const float* W1 /*[H1][H0]*/, const float* b1, in
         *reinterpret_cast<__half*>(row + (((2 + (kk >> 3)) ^ sw) << 4) + (kk & 7) * 2) = h1;
     }
 }
-// Per-particle layer-0 image: [P][chunk][hi|lo][32 rows x K0P]; row n < H0 is m0[p][n]*[W0[n][:], b0[n]],
-// row H0 is the unit vector of the bias column (the constant-1 hidden unit), the rest zero.
+// Per-particle layer-0 image: [P][chunk][X | Y][32 rows], split FP16 like layer 1: with w = b0 + b1 the row
+// of part X is [b0 | b0] and of part Y is [b1 | 0], so that against the operand row [a0 | a1]
+// X gives a0*b0 + a1*b0 and Y gives a0*b1.  Row n < H0 is m0[p][n]*[W0[n][:], b0[n]], row H0 is the unit
+// vector of the bias column (the constant-1 hidden unit), the rest zero.
 template <int K0P>
 __global__ void prep_w0_kernel(const float* W0 /*[H0][K0]*/, const float* b0, const float* mask0 /*[P][H0]*/, int P,
                                int H0, int K0, unsigned char* img) {
@@ -297,11 +291,13 @@ __global__ void prep_w0_kernel(const float* W0 /*[H0][K0]*/, const float* b0, co
         float w = 0.f;
         if (n < H0) w = mask0[(size_t)p * H0 + n] * (k < K0 ? W0[(size_t)n * K0 + k] : (k == K0 ? b0[n] : 0.f));
         else if (n == H0) w = k == K0 ? 1.f : 0.f;
-        float hi, lo;
-        split_tf32(w, hi, lo);
+        const __half h0 = __float2half_rn(w);
+        const __half h1 = __float2half_rn(w - __half2float(h0));
         unsigned char* base = img + (size_t)p * C::W0_BYTES + (size_t)j * C::W0_CHUNK;
-        *reinterpret_cast<float*>(base + swz<C::ROWB0>(rr, k)) = hi;
-        *reinterpret_cast<float*>(base + C::W0_CHUNK_PART + swz<C::ROWB0>(rr, k)) = lo;
+        *reinterpret_cast<__half*>(base + swz_byte<C::ROWB0>(rr, 2 * k)) = h0;
+        *reinterpret_cast<__half*>(base + swz_byte<C::ROWB0>(rr, 2 * (K0P + k))) = h0;
+        *reinterpret_cast<__half*>(base + C::W0_CHUNK_PART + swz_byte<C::ROWB0>(rr, 2 * k)) = h1;
+        *reinterpret_cast<__half*>(base + C::W0_CHUNK_PART + swz_byte<C::ROWB0>(rr, 2 * (K0P + k))) = __float2half_rn(0.f);
     }
 }
 // Per-particle output weights: W2p[p][c][o] = m1[p][c] * W2[o][c] / scale  (mean head only, o < D)
@@ -332,7 +328,7 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
     typedef Cfg<K0P, DP> C;
     constexpr int NB = C::NB, NS = C::NS, ROWB0 = C::ROWB0;
     constexpr int TD = TAN ? D + G::NU : 0, RPP = 1 + TD;     // passes per super-tile: primal + one per tangent direction
-    constexpr uint32_t IDESC1 = idesc_f16(TILE_M, TILE_N), IDESC0 = idesc_tf32(TILE_M, N0);
+    constexpr uint32_t IDESC1 = idesc_f16(TILE_M, TILE_N), IDESC0 = idesc_f16(TILE_M, N0);
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + C::ALIGN_PAD - 1) & ~(uintptr_t)(C::ALIGN_PAD - 1));
@@ -434,15 +430,12 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC0);
                     const uint32_t a0 = smem_u32(smem + C::A0_OFF + t * C::A0_BYTES);
                     const uint32_t b0 = smem_u32(smem + C::W0_OFF + t * C::W0_BYTES + j * C::W0_CHUNK);
-                    const uint64_t ahi = make_desc<ROWB0>(a0), alo = make_desc<ROWB0>(a0 + C::A0_PART);
-                    const uint64_t bhi = make_desc<ROWB0>(b0), blo = make_desc<ROWB0>(b0 + C::W0_CHUNK_PART);
-#pragma unroll
-                    for (int ks = 0; ks < K0P / 8; ++ks) {
-                        const uint64_t o = (uint64_t)(ks * 2);
-                        tc_mma_tf32(d_tmem, ahi + o, bhi + o, IDESC0, ks != 0);
-                        tc_mma_tf32(d_tmem, alo + o, bhi + o, IDESC0, 1);
-                        tc_mma_tf32(d_tmem, ahi + o, blo + o, IDESC0, 1);
-                    }
+                    const uint64_t ad = make_desc<ROWB0>(a0);
+                    const uint64_t bx = make_desc<ROWB0>(b0), by = make_desc<ROWB0>(b0 + C::W0_CHUNK_PART);
+                    // one K-step = 32 B of a row = 16 fp16: K0P = 8 -> [a0 | a1] in one step; K0P = 16 -> a0, then a1
+                    tc_mma_f16(d_tmem, ad, bx, IDESC0, 0);                          // a0*b0 (+ a1*b0)
+                    if (K0P == 16) tc_mma_f16(d_tmem, ad + 2, bx + 2, IDESC0, 1);   // a1*b0
+                    tc_mma_f16(d_tmem, ad, by, IDESC0, 1);                          // a0*b1
                     tc_commit(&acc0_full[t]);
                     ++l0cnt[t];
                     pos[t] += nk;
@@ -560,14 +553,17 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                         if (dir == D) row[DA] = sc[DA];
                     }
                 }
+                uint32_t x0[K0P / 2], x1[K0P / 2];       // fp16 pairs: x0 = fp16(row), x1 = fp16(row - x0)
 #pragma unroll
-                for (int c = 0; c < K0P / 4; ++c) {
-                    float hi[4], lo[4];
+                for (int e = 0; e < K0P / 2; ++e) {
+                    x0[e] = pack_f16(row[2 * e], row[2 * e + 1]);
+                    const float2 back = unpack_f16(x0[e]);
+                    x1[e] = pack_f16(row[2 * e] - back.x, row[2 * e + 1] - back.y);
+                }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) split_tf32(row[4 * c + e], hi[e], lo[e]);
-                    const uint32_t off = swz<ROWB0>(r, 4 * c);
-                    sts128f(A0 + off, hi[0], hi[1], hi[2], hi[3]);
-                    sts128f(A0 + C::A0_PART + off, lo[0], lo[1], lo[2], lo[3]);
+                for (int c = 0; c < K0P / 8; ++c) {      // 16-byte chunks: [x0 ...][x1 ...]
+                    sts128(A0 + swz_byte<ROWB0>(r, 16 * c), x0[4 * c], x0[4 * c + 1], x0[4 * c + 2], x0[4 * c + 3]);
+                    sts128(A0 + swz_byte<ROWB0>(r, 16 * (K0P / 8 + c)), x1[4 * c], x1[4 * c + 1], x1[4 * c + 2], x1[4 * c + 3]);
                 }
                 fence_async_smem();
                 mbar_arrive(&a0_full[t]);

@@ -640,7 +640,7 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
     cd.lZ = lZ; cd.lU = lU; cd.lL = make_layout(ly, B, N + 1, 1); cd.lLz = make_layout(ly, B, N + 1, nz);
     cd.lLu = make_layout(ly, B, N, nu); cd.lLzz = make_layout(ly, B, N + 1, nz * nz);
     cd.lLuz = make_layout(ly, B, N, nu * nz); cd.lLuu = make_layout(ly, B, N, nu * nu);
-    note_launches(6 + 2 + 3LL * N + 2);
+    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 9 : 5) + 2 + 3LL * N + 2 + (s->enc == PDDP_ENC_FULL_COVARIANCE_MATRIX ? 1 : 0));
     return cost_derivatives<T>(s->geo, s->enc, cd, c.st);
 }
 
@@ -692,7 +692,7 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     bnn_roll_select_kernel<T><<<(unsigned)(((long long)B * 32 + 127) / 128), 128, 0, c.st>>>(
         B, N, A, nz, w.J, w.Zall, w.Uall, c.active, c.bw_status, (T*)c.J_all, c.amin, (T*)c.J_new, (T*)c.Z_new,
         (T*)c.U_new, r.lZ, r.lU);
-    note_launches(6 + 2 + 2LL * N + 1);
+    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 9 : 5) + 2 + 2LL * N + 1);
     return cudaGetLastError();
 }
 

@@ -222,7 +222,7 @@ static int cost_derivs_t(const pddp_shape* s, const pddp_cost* cost, const void*
     a.lL = make_layout(ly, B, N + 1, 1); a.lLz = make_layout(ly, B, N + 1, nz);
     a.lLu = make_layout(ly, B, N, nu); a.lLzz = make_layout(ly, B, N + 1, nz * nz);
     a.lLuz = make_layout(ly, B, N, nu * nz); a.lLuu = make_layout(ly, B, N, nu * nu);
-    note_launches(a.J_opt ? 2 : 1);
+    note_launches((a.J_opt ? 2 : 1) + (s->enc == PDDP_ENC_FULL_COVARIANCE_MATRIX ? 1 : 0));
     return cuda_result(cost_derivatives<T>(s->geo, s->enc, a, st), "pddp_cost_derivatives");
 }
 

@@ -138,10 +138,23 @@ static cudaError_t fill_pair_order(int* nnz_out) {
     return cudaSuccess;
 }
 
+// zero L_zz (and L_uz) of every active site with coalesced stores; the structurally non-zero pairs are
+// then written by cost_pairs_kernel (FULL_COVARIANCE_MATRIX only)
+template <class T>
+__global__ void __launch_bounds__(256) cost_zero_kernel(const CostDerivArgs<T> a, int NZ) {
+    const int64_t site = blockIdx.x;
+    const int b = (int)(site / (a.N + 1)), t = (int)(site - (int64_t)b * (a.N + 1));
+    if (a.active && a.active[b] != 1) return;
+    for (int e = threadIdx.x; e < NZ * NZ; e += blockDim.x) a.L_zz[a.lLzz.at(b, t, e)] = T(0);
+    if (a.L_uz && t < a.N)
+        for (int e = threadIdx.x; e < NZ; e += blockDim.x) a.L_uz[a.lLuz.at(b, t, e)] = T(0);
+}
+
 template <class T, int GEO, int ENC>
 __global__ void __launch_bounds__(128) cost_pairs_kernel(const CostDerivArgs<T> a, int nnz) {
     typedef Geo<GEO> G;
-    constexpr int D = G::D, NZ = enc_size(D, ENC), NP = NZ * (NZ + 1) / 2;
+    constexpr int D = G::D, NZ = enc_size(D, ENC);
+    const int NP = ENC == ENC_FULL ? nnz : NZ * (NZ + 1) / 2;      // threads per site
     const int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t site = id / NP;
     if (site >= (int64_t)a.B * (a.N + 1)) return;
@@ -154,12 +167,6 @@ __global__ void __launch_bounds__(128) cost_pairs_kernel(const CostDerivArgs<T> 
         const int e = c_pair_order[GEO][p];
         i = e >> 8;
         j = e & 255;
-        if (p >= nnz) {                               // structurally zero pair (never a diagonal one)
-            a.L_zz[a.lLzz.at(b, t, i * NZ + j)] = T(0);
-            a.L_zz[a.lLzz.at(b, t, j * NZ + i)] = T(0);
-            if (i == 0 && a.L_uz && !terminal) a.L_uz[a.lLuz.at(b, t, j)] = T(0);
-            return;
-        }
     } else {
         while (p >= NZ - i) { p -= NZ - i; ++i; }
         j = i + p;
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(128) cost_pairs_kernel(const CostDerivArgs<T> 
     a.L_zz[a.lLzz.at(b, t, i * NZ + j)] = r.h[1];
     if (i != j) a.L_zz[a.lLzz.at(b, t, j * NZ + i)] = r.h[1];
     else a.L_z[a.lLz.at(b, t, i)] = r.g[0];
-    if (i == 0) a.L_uz && !terminal ? (void)(a.L_uz[a.lLuz.at(b, t, j)] = T(0)) : (void)0;
+    if (ENC != ENC_FULL && i == 0) a.L_uz && !terminal ? (void)(a.L_uz[a.lLuz.at(b, t, j)] = T(0)) : (void)0;
     if (i == 0 && j == 0) {
         T l = r.v;
         if (!terminal) {
@@ -203,12 +210,13 @@ __global__ void cost_sum_kernel(const CostDerivArgs<T> a) {
 template <class T, int GEO, int ENC>
 static cudaError_t launch_cost(const CostDerivArgs<T>& a, cudaStream_t s) {
     constexpr int NZ = enc_size(Geo<GEO>::D, ENC), NP = NZ * (NZ + 1) / 2;
-    const int64_t total = (int64_t)a.B * (a.N + 1) * NP;
     int nnz = NP;
     if (ENC == ENC_FULL) {
         cudaError_t e = fill_pair_order<GEO>(&nnz);
         if (e != cudaSuccess) return e;
+        cost_zero_kernel<T><<<(unsigned)((int64_t)a.B * (a.N + 1)), 256, 0, s>>>(a, NZ);
     }
+    const int64_t total = (int64_t)a.B * (a.N + 1) * nnz;
     cost_pairs_kernel<T, GEO, ENC><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a, nnz);
     if (a.J_opt) cost_sum_kernel<T><<<(a.B + 127) / 128, 128, 0, s>>>(a);
     return cudaGetLastError();

@@ -367,7 +367,7 @@ def main():
         achieved = flops / (pms[dom] / pcnt[dom] * 1e-3) / 1e12
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
         # (profiles/r1_summary.md, default workload only; null for the others)
-        traffic = {1: 36.9e6 + 3.5e6, 0: 4.6e6 + 0.2e6}[dom] if args.workload == "cartpole_bnn_b4096" else None
+        traffic = {1: 37.1e6 + 3.4e6, 0: 4.6e6 + 0.2e6}[dom] if args.workload == "cartpole_bnn_b4096" else None
         roofline = {"bound": "tensor", "kernel": ["bnn_mlp (linearise rows)", "bnn_mlp (rollout rows)"][dom],
                     "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                     "traffic": traffic, "peak_source": "bf16 dense sustained, " + peak_src,

@@ -221,6 +221,26 @@ __device__ __forceinline__ bool team_any(bool x) {
     if (TEAM == 32) return __any_sync(0xffffffffu, x);
     return __syncthreads_or(x) != 0;
 }
+// elements of shared memory per team: three nz x LD matrices + six LD vectors
+__host__ __device__ inline int backward_team_elems(int nz) {
+    const int LD = (nz + 3) & ~3;
+    return 3 * nz * LD + 6 * LD;
+}
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const double* p, double (&v)[4]) {
+    const double2 t0 = *reinterpret_cast<const double2*>(p), t1 = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(double* p, const double (&v)[4]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
 template <class T, int TEAM>
 __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(const BackwardArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -228,34 +248,46 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(
     const int b = blockIdx.x * wpb + warp;
     if (b >= a.B) return;
     if (a.active && a.active[b] == 0) return;
-    const int nz = a.nz, nn = nz * nz;
-    T* base = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (3 * nn + 6 * nz);
-    T *V = base, *Fz = base + nn, *W = base + 2 * nn;
-    T *v = base + 3 * nn, *Fu = v + nz, *wu = Fu + nz, *Quz = wu + nz, *Qz = Quz + nz, *Kt = Qz + nz;
+    // rows padded to LD (a multiple of 4) so that a thread can own a 1 x 4 strip of an output row and
+    // read its B operand with one 16-byte LDS per 4 FMAs (an element per thread needs 2 LDS per FMA,
+    // and at nz = 42 the pass was bound by shared-memory loads)
+    const int nz = a.nz, nn = nz * nz, LD = (nz + 3) & ~3, NS4 = LD / 4, nl = nz * LD;
+    const int per_team = backward_team_elems(nz);
+    T* base = reinterpret_cast<T*>(smem_raw) + (size_t)warp * per_team;
+    T *V = base, *Fz = base + nl, *W = base + 2 * nl;
+    T *v = base + 3 * nl, *Fu = v + LD, *wu = Fu + LD, *Quz = wu + LD, *Qz = Quz + LD, *Kt = Qz + LD;
+    for (int e = lane; e < 3 * nl; e += TEAM) base[e] = T(0);      // the padding columns stay zero
+    team_sync<TEAM>();
     const bool bounded = a.u_min != nullptr && a.u_max != nullptr;
     const T reg = (T)a.mu[b];
     T lo = T(0), hi = T(0);
     if (bounded) { lo = a.u_min[0]; hi = a.u_max[0]; }
 
-    for (int e = lane; e < nn; e += TEAM) V[e] = a.L_zz[a.lLzz.at(b, a.N, e)];
+    for (int e = lane; e < nn; e += TEAM) V[(e / nz) * LD + e % nz] = a.L_zz[a.lLzz.at(b, a.N, e)];
     for (int e = lane; e < nz; e += TEAM) v[e] = a.L_z[a.lLz.at(b, a.N, e)];
     team_sync<TEAM>();
     T k_next = T(0);
     bool ok = true;
     for (int t = a.N - 1; t >= 0; --t) {
-        for (int e = lane; e < nn; e += TEAM) Fz[e] = a.F_z[a.lFz.at(b, t, e)];
+        for (int e = lane; e < nn; e += TEAM) Fz[(e / nz) * LD + e % nz] = a.F_z[a.lFz.at(b, t, e)];
         for (int e = lane; e < nz; e += TEAM) Fu[e] = a.F_u[a.lFu.at(b, t, e)];
         team_sync<TEAM>();
         // W = V Fz ; wu = V Fu
-        for (int e = lane; e < nn; e += TEAM) {
-            const int i = e / nz, j = e - i * nz;
-            T s = T(0);
-            for (int kk = 0; kk < nz; ++kk) s += V[i * nz + kk] * Fz[kk * nz + j];
-            W[e] = s;
+        for (int s4 = lane; s4 < nz * NS4; s4 += TEAM) {
+            const int i = s4 / NS4, j0 = (s4 - i * NS4) * 4;
+            T acc[4] = {T(0), T(0), T(0), T(0)};
+            for (int kk = 0; kk < nz; ++kk) {
+                const T av = V[i * LD + kk];
+                T bv[4];
+                load4(Fz + kk * LD + j0, bv);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] += av * bv[c];
+            }
+            store4(W + i * LD + j0, acc);
         }
         for (int i = lane; i < nz; i += TEAM) {
             T s = T(0);
-            for (int kk = 0; kk < nz; ++kk) s += V[i * nz + kk] * Fu[kk];
+            for (int kk = 0; kk < nz; ++kk) s += V[i * LD + kk] * Fu[kk];
             wu[i] = s;
         }
         team_sync<TEAM>();
@@ -263,8 +295,8 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(
         for (int i = lane; i < nz; i += TEAM) {
             T sz = a.L_z[a.lLz.at(b, t, i)], suz = a.L_uz[a.lLuz.at(b, t, i)];
             for (int kk = 0; kk < nz; ++kk) {
-                sz += Fz[kk * nz + i] * v[kk];
-                suz += Fu[kk] * W[kk * nz + i];
+                sz += Fz[kk * LD + i] * v[kk];
+                suz += Fu[kk] * W[kk * LD + i];
             }
             Qz[i] = sz;
             Quz[i] = suz;
@@ -276,11 +308,19 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(
         }
         team_sync<TEAM>();
         // Q_zz = L_zz + Fz^T W  -> overwrites V (V is dead once W and wu exist)
-        for (int e = lane; e < nn; e += TEAM) {
-            const int i = e / nz, j = e - i * nz;
-            T s = a.L_zz[a.lLzz.at(b, t, e)];
-            for (int kk = 0; kk < nz; ++kk) s += Fz[kk * nz + i] * W[kk * nz + j];
-            V[e] = s;
+        for (int s4 = lane; s4 < nz * NS4; s4 += TEAM) {
+            const int i = s4 / NS4, j0 = (s4 - i * NS4) * 4;
+            T acc[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] = j0 + c < nz ? a.L_zz[a.lLzz.at(b, t, i * nz + j0 + c)] : T(0);
+            for (int kk = 0; kk < nz; ++kk) {
+                const T av = Fz[kk * LD + i];
+                T bv[4];
+                load4(W + kk * LD + j0, bv);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] += av * bv[c];
+            }
+            store4(V + i * LD + j0, acc);
         }
         T kt, inv;
         T ut = bounded ? a.U[a.lU.at(b, t, 0)] : T(0);
@@ -304,10 +344,10 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(
         for (int e = lane; e < nn; e += TEAM) {
             const int i = e / nz, j = e - i * nz;
             if (j < i) continue;
-            T q = T(0.5) * (V[i * nz + j] + V[j * nz + i]);
+            T q = T(0.5) * (V[i * LD + j] + V[j * LD + i]);
             T val = q + Kt[i] * Quu * Kt[j] + Kt[i] * Quz[j] + Quz[i] * Kt[j];
-            V[i * nz + j] = val;
-            V[j * nz + i] = val;
+            V[i * LD + j] = val;
+            V[j * LD + i] = val;
         }
         team_sync<TEAM>();
     }
@@ -323,7 +363,7 @@ cudaError_t backward_pass(const BackwardArgs<T>& a, int layout, cudaStream_t s) 
         else backward_thread_kernel<T, 4><<<grid, threads, 0, s>>>(a);
         return cudaGetLastError();
     }
-    const size_t per_team = (size_t)(3 * a.nz * a.nz + 6 * a.nz) * sizeof(T);
+    const size_t per_team = (size_t)backward_team_elems(a.nz) * sizeof(T);
     if (a.nz >= 24) {                                   // a CTA per problem
         if (per_team > 227 * 1024) return cudaErrorInvalidValue;
         cudaError_t e = cudaFuncSetAttribute(backward_warp_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_team);

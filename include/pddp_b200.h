@@ -94,6 +94,15 @@ typedef struct pddp_known_dynamics {
     double p[8];
 } pddp_known_dynamics;
 
+/* Input particles of step i (pddp/models/bnn/modules.py:320-358):
+ *   INFER    infer_noise_variables=True (default): step 0 uses m + eps_in[0] U, step i>0 re-uses the output
+ *            particles of step i-1 (eps = (X - m) U^-1 held constant in the derivatives)
+ *   RESAMPLE infer_noise_variables=False: X = m + eps_in[i] U(z_i) at every step
+ *   MEAN     sample_input_distribution=False: every particle starts at the mean (the covariance is ignored) */
+#define PDDP_BNN_INPUT_INFER 0
+#define PDDP_BNN_INPUT_RESAMPLE 1
+#define PDDP_BNN_INPUT_MEAN 2
+
 /* Eval-mode BNN dynamics (device pointers, element type = shape.dtype).
  * Replaces the state read by pddp/models/bnn/modules.py:200-264,287-386:
  * Linear weights (torch [out,in] row-major), persistent dropout masks [P,H],
@@ -109,6 +118,9 @@ typedef struct pddp_bnn {
     const void* eps0;     /* [P, D]  */
     const void* X_mean; const void* X_std_inv;  /* [DA+nu] or NULL */
     const void* dX_mean; const void* dX_std;    /* [D] or NULL */
+    int32_t input_mode;   /* PDDP_BNN_INPUT_* : how the input particles of step i are formed */
+    const void* eps_in;   /* [N, P, D] standardised noise of every step (PDDP_BNN_INPUT_RESAMPLE only;
+                             the reference draws eps_in[i] lazily, modules.py:321-329 -- here it is data) */
 } pddp_bnn;
 
 const char* pddp_version(void);
@@ -172,8 +184,8 @@ int pddp_accept_update(const pddp_shape* shape, const void* J_new, const int32_t
 
 /* ---- BNN dynamics ----------------------------------------------------------------------------
  * pddp_linearize_bnn replaces ilqr.forward with a factory-built BNNDynamicsModel
- * (pddp/models/bnn/modules.py:287-386 + 200-264, eval mode, use_predicted_std=False,
- * infer_noise_variables=True, sample_input_distribution=True); pddp_rollout_bnn replaces
+ * (pddp/models/bnn/modules.py:287-386 + 200-264, eval mode, use_predicted_std=False; the
+ * infer_noise_variables / sample_input_distribution options are pddp_bnn.input_mode); pddp_rollout_bnn replaces
  * _control_law + _trajectory_cost for the same model.  `workspace` is a device scratch buffer of
  * at least pddp_bnn_workspace_bytes(...) bytes.                                               */
 int64_t pddp_bnn_workspace_bytes(const pddp_shape* shape, const pddp_bnn* bnn, int32_t A);

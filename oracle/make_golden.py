@@ -64,7 +64,10 @@ def bnn_spec(model, model_cls, dtype):
         elif isinstance(mod, BDropout):
             masks.append(mod.noise.data.clone())
     vec = lambda b: None if b.dim() == 0 else b.data.clone()
-    return O.BNNSpec(layers, masks, model.eps_in[0].data.clone(), model_cls.state_size,
+    # (sample_input_distribution=False never draws eps_in: zeros of the right shape then)
+    eps0 = model.eps_in[0].data.clone() if 0 in model.eps_in else torch.zeros(
+        model.n_particles, model_cls.state_size, dtype=layers[0][0].dtype)
+    return O.BNNSpec(layers, masks, eps0, model_cls.state_size,
                      model_cls.action_size, tuple(model_cls.angular_indices.tolist()),
                      tuple(model_cls.non_angular_indices.tolist()), vec(model.X_mean),
                      vec(model.X_std_inv), vec(model.dX_mean), vec(model.dX_std)).to(dtype)
@@ -87,10 +90,13 @@ def close(a, b, tol, what):
 
 
 NAMES = "Z F_z F_u L L_z L_u L_zz L_uz L_uu".split()
+ONLY = sys.argv[1:]
 
 
 def run_case(tag, name, enc, dtype, N, seed, bnn=None, bounded=False, reg=1.0, n_alpha=10,
-             fit_iters=0):
+             fit_iters=0, input_mode="infer"):
+    if ONLY and not any(o in tag for o in ONLY):     # python make_golden.py <substring> ...: subset
+        return True
     torch.manual_seed(seed)
     model_cls, cost_cls, spec_fn, _, umax = PROBLEMS[name]
     tol = 1e-9 if dtype == torch.float64 else 2e-4
@@ -110,6 +116,10 @@ def run_case(tag, name, enc, dtype, N, seed, bnn=None, bounded=False, reg=1.0, n
             model.model.fc_out.bias *= scale_out
         model.eval()
     model_opts = {} if bnn is None else {"use_predicted_std": False, "infer_noise_variables": True}
+    if input_mode == "resample":
+        model_opts["infer_noise_variables"] = False
+    elif input_mode == "mean":
+        model_opts["sample_input_distribution"] = False
     z0 = z0_for(name, enc, dtype, seed)
     U = (0.1 * torch.randn(N, model_cls.action_size)).to(dtype)
     if bounded:
@@ -126,6 +136,10 @@ def run_case(tag, name, enc, dtype, N, seed, bnn=None, bounded=False, reg=1.0, n
                                         " bounded" if bounded else ""))
     lin = R.forward(z0, U.clone(), model, cost, enc, True, model_opts, {}, u_min=u_min,
                     u_max=u_max)
+    if input_mode != "infer":
+        odyn.input_mode = input_mode
+        if input_mode == "resample":      # the reference drew eps_in[i] for every step during forward()
+            odyn.eps_in = torch.stack([model.eps_in[i].data.clone() for i in range(N)]).to(dtype)
     olin = O.linearize(z0, U, odyn, ospec_cost, enc, u_min, u_max)
     for n, a, b in zip(NAMES, olin, lin):
         ok &= close(a, b, tol, n)
@@ -169,6 +183,9 @@ def run_case(tag, name, enc, dtype, N, seed, bnn=None, bounded=False, reg=1.0, n
         for i, m in enumerate(odyn.masks):
             fx["mask%d" % i] = m
         fx["eps0"] = odyn.eps0
+        fx["input_mode"] = {"infer": 0, "resample": 1, "mean": 2}[input_mode]
+        if odyn.eps_in is not None:
+            fx["eps_in"] = odyn.eps_in
 
     if fit_iters:
         class Env:
@@ -237,6 +254,15 @@ def main():
                    bnn=([32, 32], 12, 0.05))
     ok &= run_case("bnn_cartpole_std_small_f64", "cartpole", E.STANDARD_DEVIATION_ONLY, f64, 5, 32,
                    bnn=([32, 32], 12, 0.05))
+    # BNN input-particle options: infer_noise_variables=False, sample_input_distribution=False
+    ok &= run_case("bnn_cartpole_ut_resample_small_f64", "cartpole", E.UPPER_TRIANGULAR_CHOLESKY, f64, 5,
+                   33, bnn=([32, 32], 12, 0.05), input_mode="resample")
+    ok &= run_case("bnn_cartpole_ut_mean_small_f64", "cartpole", E.UPPER_TRIANGULAR_CHOLESKY, f64, 5,
+                   34, bnn=([32, 32], 12, 0.05), input_mode="mean")
+    ok &= run_case("bnn_double_cartpole_full_resample_small_f64", "double_cartpole",
+                   E.FULL_COVARIANCE_MATRIX, f64, 4, 35, bnn=([32, 32], 16, 0.05), input_mode="resample")
+    ok &= run_case("bnn_cartpole_ut_resample_f32", "cartpole", E.UPPER_TRIANGULAR_CHOLESKY, f32, 4, 36,
+                   bnn=([200, 200], 50, 0.02), input_mode="resample")
     print("ALL OK" if ok else "SOME MISMATCH")
     return 0 if ok else 1
 

@@ -373,7 +373,7 @@ def _double_cartpole(p, x, u):
 _KNOWN = {"pendulum": _pendulum, "cartpole": _cartpole, "double_cartpole": _double_cartpole}
 
 
-def known_step(spec, z, u, enc, carry=None):
+def known_step(spec, z, u, enc, carry=None, i=None):
     """Mean through the ODE step, variance passed through unchanged."""
     mean = _KNOWN[spec.kind](spec.params, decode_mean(z, enc, spec.D), u)
     return encode(mean, V=decode_var(z, enc, spec.D), enc=enc), None
@@ -397,6 +397,12 @@ class BNNSpec:
     X_std_inv: Optional[torch.Tensor] = None   # [Da+nu] or None (1)
     dX_mean: Optional[torch.Tensor] = None     # [D] or None (0)
     dX_std: Optional[torch.Tensor] = None      # [D] or None (1)
+    # input particles (ref: modules.py:320-358).  "infer": eps of step i > 0 is inferred from the previous
+    # output particles (infer_noise_variables=True, the default); "resample": eps_in[i] of every step
+    # (infer_noise_variables=False); "mean": every particle starts at the mean
+    # (sample_input_distribution=False)
+    input_mode: str = "infer"
+    eps_in: Optional[torch.Tensor] = None      # [N, P, D], eps_in[0] == eps0 ("resample" only)
 
     @property
     def P(self):
@@ -407,7 +413,7 @@ class BNNSpec:
         return BNNSpec([(W.to(dtype), b.to(dtype)) for W, b in self.weights],
                        [m.to(dtype) for m in self.masks], self.eps0.to(dtype), self.D, self.nu,
                        tuple(self.ang), tuple(self.nonang), c(self.X_mean), c(self.X_std_inv),
-                       c(self.dX_mean), c(self.dX_std))
+                       c(self.dX_mean), c(self.dX_std), self.input_mode, c(self.eps_in))
 
 
 def bnn_particles(spec, X, u):
@@ -429,7 +435,7 @@ def bnn_particles(spec, X, u):
     return X + dx
 
 
-def bnn_step(spec, z, u, enc, carry=None):
+def bnn_step(spec, z, u, enc, carry=None, i=None):
     """One moment-matched BNN step on rows z:[R,nz], u:[R,nu]; carry = previous particles [R,P,D].
 
     ref: models/bnn/modules.py:287-386 with sample_input_distribution=True,
@@ -442,7 +448,11 @@ def bnn_step(spec, z, u, enc, carry=None):
     D, P = spec.D, spec.P
     m = decode_mean(z, enc, D)
     Uc = decode_covar_sqrt(z, enc, D)                                    # [R,D,D] upper
-    if carry is None:
+    if spec.input_mode == "mean":
+        eps = torch.zeros(z.shape[0], P, D, dtype=z.dtype)
+    elif spec.input_mode == "resample":
+        eps = spec.eps_in[i].unsqueeze(0).expand(z.shape[0], P, D)
+    elif carry is None:
         eps = spec.eps0.unsqueeze(0).expand(z.shape[0], P, D)
     else:
         delta = (carry - m.unsqueeze(-2)).detach()                       # [R,P,D]
@@ -491,13 +501,13 @@ def cost_derivatives(cost, z, u, terminal, enc):
     return l, g0[:nz], g0[nz:], H[:nz, :nz].detach(), H[nz:, :nz].detach(), H[nz:, nz:].detach()
 
 
-def dynamics_derivatives(dyn, z, u, enc, carry):
+def dynamics_derivatives(dyn, z, u, enc, carry, i=None):
     """z' and d z'/d[z,u] via nz replicated rows (ref: utils/evaluation.py:242-288)."""
     nz = z.shape[-1]
     zu = torch.cat([z, u], -1).detach()
     rows = zu.expand(nz, -1).clone().requires_grad_()
     c = None if carry is None else carry[:1].expand(nz, -1, -1)
-    zn, carry = step_fn(dyn)(dyn, rows[:, :nz], rows[:, nz:], enc, c)
+    zn, carry = step_fn(dyn)(dyn, rows[:, :nz], rows[:, nz:], enc, c, i=i)
     J, = torch.autograd.grad(zn, rows, torch.eye(nz, dtype=z.dtype))
     return zn[0].detach(), J[:, :nz], J[:, nz:], (None if carry is None else carry[:1])
 
@@ -518,7 +528,7 @@ def linearize(z0, U, dyn, cost, enc, u_min=None, u_max=None):
         u = U[t] if u_min is None or u_max is None else clamp(U[t], u_min, u_max)
         L[t], L_z[t], L_u[t], L_zz[t], L_uz[t], L_uu[t] = cost_derivatives(cost, Z[t], u, False,
                                                                            enc)
-        Z[t + 1], F_z[t], F_u[t], carry = dynamics_derivatives(dyn, Z[t], u, enc, carry)
+        Z[t + 1], F_z[t], F_u[t], carry = dynamics_derivatives(dyn, Z[t], u, enc, carry, i=t)
     L[N], L_z[N], _, L_zz[N], _, _ = cost_derivatives(cost, Z[N], None, True, enc)
     return Z, F_z, F_u, L, L_z, L_u, L_zz, L_uz, L_uu
 
@@ -647,7 +657,7 @@ def rollout(dyn, Z, U, k, K, alphas, enc, u_min=None, u_max=None):
         u = U[t] + du
         if u_min is not None and u_max is not None:
             u = clamp(u, u_min, u_max)
-        Z_new[t + 1], carry = f(dyn, Z_new[t], u, enc, carry)
+        Z_new[t + 1], carry = f(dyn, Z_new[t], u, enc, carry, i=t)
         U_new[t] = u
     return Z_new, U_new
 

@@ -14,6 +14,7 @@ PROBLEM_MAJOR, BATCH_INNER = 0, 1
 GEO_PENDULUM, GEO_CARTPOLE, GEO_DOUBLE_CARTPOLE = 0, 1, 2
 MAX_DA, MAX_NU = 8, 1
 STATUS_NOT_PD, STATUS_NAN = 1, 2
+BNN_INPUT_INFER, BNN_INPUT_RESAMPLE, BNN_INPUT_MEAN = 0, 1, 2
 
 GEO_INFO = {  # geo -> (D, nu, angular, non-angular)
     GEO_PENDULUM: (2, 1, (0,), (1,)),
@@ -39,7 +40,8 @@ class KnownDynamics(C.Structure):
 class BNN(C.Structure):
     _fields_ = [("P", C.c_int32), ("H0", C.c_int32), ("H1", C.c_int32)] + [
         (n, C.c_void_p) for n in ("W0", "b0", "W1", "b1", "W2", "b2", "mask0", "mask1", "eps0",
-                                  "X_mean", "X_std_inv", "dX_mean", "dX_std")]
+                                  "X_mean", "X_std_inv", "dX_mean", "dX_std")] + [
+        ("input_mode", C.c_int32), ("eps_in", C.c_void_p)]
 
 
 _P = C.c_void_p

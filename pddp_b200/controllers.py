@@ -45,11 +45,11 @@ class Controller(torch.nn.Module):
         raise NotImplementedError
 
 
-def _solver_for(model, cost, encoding, B, N, dtype, device, max_alphas=16):
-    if cost.geometry() != model.descriptor().geo:
+def _solver_for(model, cost, encoding, B, N, dtype, device, max_alphas=16, model_opts={}):
+    desc = model.descriptor(model_opts, N) if getattr(model, "is_bnn", False) else model.descriptor()
+    if cost.geometry() != desc.geo:
         raise ValueError("model and cost disagree on the state geometry")
-    return BatchedSolver(model.descriptor(), cost.constants(), encoding, B, N, dtype=dtype, device=device,
-                         max_alphas=max_alphas)
+    return BatchedSolver(desc, cost.constants(), encoding, B, N, dtype=dtype, device=device, max_alphas=max_alphas)
 
 
 def _bounds(u_min, u_max):
@@ -83,7 +83,8 @@ class iLQRController(Controller):
         s = self._solver
         if (s is None or (s.B, s.N, int(s.enc), s.dtype, s.device) != (B, N, int(encoding), dtype, device)
                 or s.max_alphas < n_alphas):
-            self._solver = _solver_for(self.model, self.cost, encoding, B, N, dtype, device, max(16, n_alphas))
+            self._solver = _solver_for(self.model, self.cost, encoding, B, N, dtype, device, max(16, n_alphas),
+                                       self._model_opts)
         return self._solver
 
     def _results(self, s):
@@ -266,7 +267,7 @@ def forward(z0, U, model, cost, encoding=StateEncoding.DEFAULT, batch_rollout=Tr
     check_model_opts(model, model_opts)
     _lib.require_cuda(U, "U")
     u_min, u_max = _bounds(u_min, u_max)
-    s = _solver_for(model, cost, encoding, 1, U.shape[0], U.dtype, U.device)
+    s = _solver_for(model, cost, encoding, 1, U.shape[0], U.dtype, U.device, model_opts=model_opts)
     s.set_problem(z0.reshape(1, -1).to(U.dtype), U.unsqueeze(0), u_min, u_max)
     s.linearize(use_active=False)
     return tuple(s.matrices(n)[0].clone() for n in LIN_NAMES)
@@ -345,7 +346,7 @@ def _control_law(model, Z, U, k, K, alpha, encoding=StateEncoding.DEFAULT, model
     DA = model.state_size + len(model.angular_indices)
     cost = cost or QRCost(torch.zeros(DA, DA), torch.zeros(1, 1), state_size=model.state_size,
                           angular_indices=model.angular_indices.tolist())
-    s = _solver_for(model, cost, encoding, 1, U.shape[0], U.dtype, U.device)
+    s = _solver_for(model, cost, encoding, 1, U.shape[0], U.dtype, U.device, model_opts=model_opts)
     Zs, Us = [], []
     for a in alpha.reshape(-1):
         s.set_problem(Z[0].reshape(1, -1), U.unsqueeze(0), u_min, u_max, alphas=a.reshape(1))

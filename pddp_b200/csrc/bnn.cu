@@ -34,27 +34,34 @@ __global__ void bnn_transpose_kernel(const T* W, int out, int in, int out_used, 
 }
 
 // ------------------------------------------------------------------------------------------
-// particles of step 0: X_p = m + eps0_p U(z0), one thread per (group s, particle p)
+// input particles of step t: X_p = m + eps_p U(z_t), one thread per (group s, particle p); eps == nullptr
+// puts every particle on the mean (sample_input_distribution=False).  The encoded state of group s is
+// row (s / zdiv, t) of z, its status word is status[s / sdiv].   ref: modules.py:320-358
 // ------------------------------------------------------------------------------------------
 template <class T, int GEO, int ENC>
-__global__ void bnn_init_particles_kernel(const T* z, Layout lz, int groups_per_problem, long long S, int P,
-                                          const T* eps0, T* X, int32_t* status) {
+__global__ void bnn_init_particles_kernel(const T* z, Layout lz, int t, int zdiv, int sdiv, long long S, int P,
+                                          const T* eps, const int32_t* active, int active_skip_other,
+                                          const int32_t* bw_status, T* X, int32_t* status) {
     constexpr int D = Geo<GEO>::D, NZ = enc_size(D, ENC);
     const long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (id >= S * P) return;
     const long long s = id / P;
     const int p = (int)(id - s * P);
-    const int b = (int)(s / groups_per_problem);
+    const int b = (int)(s / zdiv), sb = (int)(s / sdiv);
+    if (active && (active_skip_other ? active[sb] != 1 : active[sb] == 0)) return;
+    if (bw_status && bw_status[sb] != 0) return;
     T zz[NZ];
 #pragma unroll
-    for (int e = 0; e < NZ; ++e) zz[e] = z[lz.at(b, 0, e)];
+    for (int e = 0; e < NZ; ++e) zz[e] = z[lz.at(b, t, e)];
     T U[D][D];
-    if (!load_factor<D, ENC, T>(zz, U) && status) status[b] |= 2;
+    if (!load_factor<D, ENC, T>(zz, U) && status) atomicOr(&status[sb], 2);
 #pragma unroll
     for (int c = 0; c < D; ++c) {
         T v = zz[c];
+        if (eps) {
 #pragma unroll
-        for (int r = 0; r <= c; ++r) v += eps0[p * D + r] * U[r][c];
+            for (int r = 0; r <= c; ++r) v += eps[p * D + r] * U[r][c];
+        }
         X[id * D + c] = v;
     }
 }
@@ -601,8 +608,16 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
     T* Z = (T*)c.Z;
     bnn_set_z0_kernel<T><<<(B * nz + 255) / 256, 256, 0, c.st>>>(B, nz, (const T*)c.z0, Z, lZ, c.active);
     const long long total = (long long)B * P;
-    bnn_init_particles_kernel<T, GEO, ENC><<<(unsigned)((total + 127) / 128), 128, 0, c.st>>>(
-        Z, lZ, 1, B, P, net.eps0, w.Xa, c.status);
+    // input particles (ref: modules.py:320-358): INFER carries them from step to step, RESAMPLE / MEAN rebuild
+    // them from z_t at every step
+    const int mode = c.n->input_mode;
+    auto eps_of = [&](int t) -> const T* {
+        return mode == PDDP_BNN_INPUT_MEAN ? nullptr
+             : mode == PDDP_BNN_INPUT_RESAMPLE ? (const T*)c.n->eps_in + (size_t)t * P * D : net.eps0;
+    };
+    const unsigned igrid = (unsigned)((total + 127) / 128);
+    bnn_init_particles_kernel<T, GEO, ENC><<<igrid, 128, 0, c.st>>>(Z, lZ, 0, 1, 1, B, P, eps_of(0), nullptr, 0,
+                                                                    nullptr, w.Xa, c.status);
     CK(cudaGetLastError());
 
     MomentLinArgs<T> m;
@@ -619,6 +634,9 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
     for (int t = 0; t < N; ++t) {
         bnn_lin_control_kernel<T><<<(B + 127) / 128, 128, 0, c.st>>>(B, t, (const T*)c.U, lU, (const T*)c.u_min,
                                                                   (const T*)c.u_max, w.ucur, (T*)c.L_u);
+        if (mode != PDDP_BNN_INPUT_INFER && t > 0)
+            bnn_init_particles_kernel<T, GEO, ENC><<<igrid, 128, 0, c.st>>>(Z, lZ, t, 1, 1, B, P, eps_of(t), c.active, 1,
+                                                                            nullptr, cur, c.status);
         a.X = cur; a.Xn = nxt;
         prof_begin(PROF_MLP_LIN, c.st);
         CK((launch_mlp<T, GEO, true>(a, w.im, c.st)));
@@ -640,7 +658,8 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
     cd.lZ = lZ; cd.lU = lU; cd.lL = make_layout(ly, B, N + 1, 1); cd.lLz = make_layout(ly, B, N + 1, nz);
     cd.lLu = make_layout(ly, B, N, nu); cd.lLzz = make_layout(ly, B, N + 1, nz * nz);
     cd.lLuz = make_layout(ly, B, N, nu * nz); cd.lLuu = make_layout(ly, B, N, nu * nu);
-    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 9 : 5) + 2 + 3LL * N + 2 + (s->enc == PDDP_ENC_FULL_COVARIANCE_MATRIX ? 1 : 0));
+    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 9 : 5) + 2 + 3LL * N + 2 + (s->enc == PDDP_ENC_FULL_COVARIANCE_MATRIX ? 1 : 0)
+                  + (mode != PDDP_BNN_INPUT_INFER ? N - 1 : 0));
     return cost_derivatives<T>(s->geo, s->enc, cd, c.st);
 }
 
@@ -669,8 +688,16 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     r.Zall = w.Zall; r.Uall = w.Uall; r.ucur = w.ucur; r.J = w.J; r.status = c.status;
     r.lZ = make_layout(ly, B, N + 1, nz); r.lU = make_layout(ly, B, N, nu);
     r.lk = make_layout(ly, B, N, nu); r.lK = make_layout(ly, B, N, nu * nz);
-    bnn_init_particles_kernel<T, GEO, ENC><<<(unsigned)((total + 127) / 128), 128, 0, c.st>>>(
-        r.Z, r.lZ, A, S, P, net.eps0, w.Xa, c.status);
+    constexpr int D = G::D;
+    const int mode = c.n->input_mode;
+    auto eps_of = [&](int t) -> const T* {
+        return mode == PDDP_BNN_INPUT_MEAN ? nullptr
+             : mode == PDDP_BNN_INPUT_RESAMPLE ? (const T*)c.n->eps_in + (size_t)t * P * D : net.eps0;
+    };
+    const unsigned igrid = (unsigned)((total + 127) / 128);
+    const Layout lZall = make_layout(PDDP_PROBLEM_MAJOR, (int)S, N + 1, nz);
+    bnn_init_particles_kernel<T, GEO, ENC><<<igrid, 128, 0, c.st>>>(r.Z, r.lZ, 0, A, A, S, P, eps_of(0), nullptr, 0,
+                                                                    nullptr, w.Xa, c.status);
     const unsigned rgrid = (unsigned)((S + 31) / 32);
     r.t = -1; r.Xn = w.Xa;
     bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 256, 0, c.st>>>(r);
@@ -687,12 +714,15 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
         prof_begin(PROF_ROLL_STEP, c.st);
         bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 256, 0, c.st>>>(r);
         prof_end(PROF_ROLL_STEP, c.st);
+        if (mode != PDDP_BNN_INPUT_INFER && t + 1 < N)      // candidate particles of step t+1 from the z' just encoded
+            bnn_init_particles_kernel<T, GEO, ENC><<<igrid, 128, 0, c.st>>>(w.Zall, lZall, t + 1, 1, A, S, P, eps_of(t + 1),
+                                                                            c.active, 0, c.bw_status, nxt, c.status);
         T* tmp = cur; cur = nxt; nxt = tmp;
     }
     bnn_roll_select_kernel<T><<<(unsigned)(((long long)B * 32 + 127) / 128), 128, 0, c.st>>>(
         B, N, A, nz, w.J, w.Zall, w.Uall, c.active, c.bw_status, (T*)c.J_all, c.amin, (T*)c.J_new, (T*)c.Z_new,
         (T*)c.U_new, r.lZ, r.lU);
-    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 9 : 5) + 2 + 2LL * N + 1);
+    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 9 : 5) + 2 + 2LL * N + 1 + (mode != PDDP_BNN_INPUT_INFER ? N - 1 : 0));
     return cudaGetLastError();
 }
 
@@ -735,6 +765,10 @@ static int check_bnn(const pddp_shape* s, const pddp_bnn* n) {
     if (n->H0 < 1 || n->H1 < 1 || n->H0 > 256 || n->H1 > 256) return pddp_capi_fail(PDDP_E_UNSUPPORTED, "hidden widths must be in [1,256]");
     if (!n->W0 || !n->b0 || !n->W1 || !n->b1 || !n->W2 || !n->b2 || !n->mask0 || !n->mask1 || !n->eps0)
         return pddp_capi_fail(PDDP_E_BADARG, "bnn: NULL weight / mask / eps0 pointer");
+    if (n->input_mode < PDDP_BNN_INPUT_INFER || n->input_mode > PDDP_BNN_INPUT_MEAN)
+        return pddp_capi_fail(PDDP_E_BADARG, "bnn: input_mode must be PDDP_BNN_INPUT_INFER / RESAMPLE / MEAN");
+    if (n->input_mode == PDDP_BNN_INPUT_RESAMPLE && !n->eps_in)
+        return pddp_capi_fail(PDDP_E_BADARG, "bnn: PDDP_BNN_INPUT_RESAMPLE needs eps_in[N,P,D]");
     return 0;
 }
 

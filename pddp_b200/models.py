@@ -196,7 +196,7 @@ def bnn_dynamics_model_factory(state_size, action_size, hidden_features, angular
                 drop = getattr(ref_model.model, "drop_%d" % li)
                 mask = getattr(drop, "concrete_noise", None)
                 getattr(self.model, "drop_%d" % li).mask = (drop.noise if mask is None else mask).detach().clone()
-            self.eps_in = {0: ref_model.eps_in[0].detach().clone()}
+            self.eps_in = {int(i): e.detach().clone() for i, e in ref_model.eps_in.items()}
             self.n_particles = self.eps_in[0].shape[0]
             for n in ("X_mean", "X_std", "X_std_inv", "dX_mean", "dX_std", "dX_std_inv"):
                 setattr(self, n, getattr(ref_model, n).detach().clone())
@@ -230,15 +230,32 @@ def bnn_dynamics_model_factory(state_size, action_size, hidden_features, angular
                 opt.step()
             self.resample()
 
-        def descriptor(self):
+        def descriptor(self, model_opts=None, N=None):
+            """BNNDynamics for the kernels.  model_opts selects how input particles are formed
+            (ref: modules.py:320-358): infer_noise_variables=False needs eps_in[i] for every step
+            i < N; steps the model has not seen yet are drawn here, in step order, the way the
+            reference draws them on first use (modules.py:321-329)."""
+            opts = model_opts or {}
             if 0 not in self.eps_in:
                 self.resample()
+            mode, eps_in = _lib.BNN_INPUT_INFER, None
+            if not opts.get("sample_input_distribution", True):
+                mode = _lib.BNN_INPUT_MEAN
+            elif not opts.get("infer_noise_variables", True):
+                mode = _lib.BNN_INPUT_RESAMPLE
+                if N is None:
+                    raise ValueError("infer_noise_variables=False needs the horizon N to lay out eps_in")
+                for i in range(N):
+                    if i not in self.eps_in:
+                        eps = torch.randn(self.n_particles, _state_size)
+                        self.eps_in[i] = (eps - eps.mean(0)) / eps.std(0)
+                eps_in = torch.stack([self.eps_in[i] for i in range(N)])
             m = self.model
             vec = lambda b: None if b.dim() == 0 else b
             return BNNDynamics(geo, [m.fc_0.weight, m.fc_1.weight, m.fc_out.weight],
                                [m.fc_0.bias, m.fc_1.bias, m.fc_out.bias], [m.drop_0.mask, m.drop_1.mask],
                                self.eps_in[0], vec(self.X_mean), vec(self.X_std_inv), vec(self.dX_mean),
-                               vec(self.dX_std))
+                               vec(self.dX_std), input_mode=mode, eps_in=eps_in)
 
     return BNNDynamicsModel
 
@@ -254,11 +271,11 @@ def _augment(x, ang):
 
 
 def check_model_opts(model, model_opts):
-    """The kernels implement exactly one option set (the one every reference example uses)."""
+    """Options the kernels implement: infer_noise_variables and sample_input_distribution either way
+    (BNNDynamics.input_mode); the rest only at the value every reference example uses."""
     if not getattr(model, "is_bnn", False):
         return
-    want = dict(use_predicted_std=False, infer_noise_variables=True, sample_input_distribution=True, resample=False,
-                independent_noise=False)
+    want = dict(use_predicted_std=False, resample=False, independent_noise=False)
     for k, v in model_opts.items():
         if k in want and bool(v) != want[k]:
             raise NotImplementedError("pddp_b200: model option %s=%r is not built (SURVEY 8f rank 2); supported: %r"

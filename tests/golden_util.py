@@ -65,7 +65,15 @@ class Fixture:
         n_layers = sum(1 for k in self.raw if k.startswith("W"))
         weights = [(self.t("W%d" % i), self.t("b%d" % i)) for i in range(n_layers)]
         masks = [self.t("mask%d" % i) for i in range(n_layers - 1)]
-        return O.BNNSpec(weights, masks, self.t("eps0"), self.D, self.nu, self.ang, self.nonang)
+        spec = O.BNNSpec(weights, masks, self.t("eps0"), self.D, self.nu, self.ang, self.nonang)
+        spec.input_mode = self.input_mode
+        spec.eps_in = self.t("eps_in") if self.has("eps_in") else None
+        return spec
+
+    @property
+    def input_mode(self):
+        """BNN input-particle option the reference ran with (absent in the older fixtures = default)."""
+        return ("infer", "resample", "mean")[int(self.raw["input_mode"])] if self.has("input_mode") else "infer"
 
 
 def rel_err(a, b):

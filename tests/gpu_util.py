@@ -23,7 +23,8 @@ def dynamics_from_fixture(fx, device="cuda"):
     from pddp_b200.solver import BNNDynamics
     return BNNDynamics(GEO[fx.name], [fx.t("W0"), fx.t("W1"), fx.t("W2")],
                        [fx.t("b0"), fx.t("b1"), fx.t("b2")], [fx.t("mask0"), fx.t("mask1")],
-                       fx.t("eps0"))
+                       fx.t("eps0"), input_mode=("infer", "resample", "mean").index(fx.input_mode),
+                       eps_in=fx.t("eps_in") if fx.has("eps_in") else None)
 
 
 def solver_from_fixture(fx, B=1, layout=None):

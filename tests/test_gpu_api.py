@@ -25,6 +25,11 @@ def build(fx):
         model.model.drop_0.mask, model.model.drop_1.mask = fx.t("mask0"), fx.t("mask1")
         model.eps_in = {0: fx.t("eps0")}
         opts = {"use_predicted_std": False, "infer_noise_variables": True}
+        if fx.input_mode == "resample":       # ref: modules.py:320-358 -- eps_in[i] of every step, as the reference drew them
+            model.eps_in = {i: e for i, e in enumerate(fx.t("eps_in"))}
+            opts["infer_noise_variables"] = False
+        elif fx.input_mode == "mean":
+            opts["sample_input_distribution"] = False
     else:
         cls = {"pendulum": models.PendulumDynamicsModel, "cartpole": models.CartpoleDynamicsModel,
                "double_cartpole": models.DoubleCartpoleDynamicsModel}[fx.name]
@@ -34,7 +39,8 @@ def build(fx):
 
 
 TAGS = ["known_pendulum_ign_f64", "known_cartpole_ut_bounded_f64", "known_double_cartpole_full_f64",
-        "bnn_cartpole_ut_small_f64", "bnn_double_cartpole_full_small_f64", "bnn_cartpole_ut_bounded_f64"]
+        "bnn_cartpole_ut_small_f64", "bnn_double_cartpole_full_small_f64", "bnn_cartpole_ut_bounded_f64",
+        "bnn_cartpole_ut_resample_small_f64", "bnn_cartpole_ut_mean_small_f64"]
 
 
 @pytest.mark.parametrize("tag", TAGS)

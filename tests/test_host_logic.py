@@ -32,7 +32,7 @@ def test_struct_layouts():
     assert ctypes.sizeof(_lib.Shape) == 8 * 4
     assert ctypes.sizeof(_lib.Cost) == (64 + 64 + 1 + 8 + 1) * 8
     assert ctypes.sizeof(_lib.KnownDynamics) == 64
-    assert ctypes.sizeof(_lib.BNN) == 16 + 13 * 8
+    assert ctypes.sizeof(_lib.BNN) == 16 + 13 * 8 + 8 + 8     # + input_mode (padded) + eps_in
 
 
 def test_no_cpu_fallback():

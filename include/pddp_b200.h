@@ -63,7 +63,7 @@ extern "C" {
 #define PDDP_E_UNSUPPORTED (-2)
 
 #define PDDP_MAX_DA 8
-#define PDDP_MAX_NU 1
+#define PDDP_MAX_NU 4
 
 /* Problem shape shared by all calls. */
 typedef struct pddp_shape {
@@ -74,7 +74,7 @@ typedef struct pddp_shape {
     int32_t B;       /* independent problems */
     int32_t N;       /* horizon */
     int32_t nz;      /* encoded state size (must equal the encoding's size for geo's D) */
-    int32_t nu;      /* action size (1) */
+    int32_t nu;      /* action size (1 for the three pendulum-family geometries; pddp_backward: 1..PDDP_MAX_NU) */
 } pddp_shape;
 
 /* Constants of a QRCost on the angle-augmented state (host memory, doubles, row-major DAxDA).
@@ -143,7 +143,10 @@ int pddp_linearize_known(const pddp_shape* shape, const pddp_known_dynamics* dyn
 
 /* ---- backward Riccati pass ------------------------------------------------------------------
  * Replaces pddp.controllers.ilqr.backward + Q (ilqr.py:489-674, default V_zz_reg=False branch)
- * and, with bounds, pddp.utils.constraint.boxqp for nu==1 (constraint.py:150-266).
+ * and, with bounds, pddp.utils.constraint.boxqp (constraint.py:150-266).  This call only needs the
+ * derivative tensors: shape.geo / shape.enc are ignored and any nz >= 1, 1 <= nu <= PDDP_MAX_NU is
+ * accepted (nu > 1: eigen-clipping by Jacobi rotations and the n-dimensional projected-Newton box QP;
+ * u_min / u_max are [nu] vectors).
  *   in : the derivative tensors above, mu[B] (per-problem regularisation, float64), U,
  *        u_min/u_max or NULL
  *   out: k[B,N,nu]  K[B,N,nu*nz]  status[B] = PDDP_STATUS_NOT_PD where the reference would raise */

@@ -30,6 +30,8 @@ from pddp.examples.cartpole.model import CartpoleDynamicsModel  # noqa: E402
 from pddp.examples.cartpole.cost import CartpoleCost  # noqa: E402
 from pddp.examples.double_cartpole.model import DoubleCartpoleDynamicsModel  # noqa: E402
 from pddp.examples.double_cartpole.cost import DoubleCartpoleCost  # noqa: E402
+from pddp.examples.rendezvous.model import RendezvousDynamicsModel  # noqa: E402
+from pddp.examples.rendezvous.cost import RendezvousCost  # noqa: E402
 from pddp.models.bnn import bnn_dynamics_model_factory  # noqa: E402
 from pddp.models.bnn.modules import BDropout, CDropout  # noqa: E402
 from pddp.utils.gaussian_variable import GaussianVariable  # noqa: E402
@@ -41,13 +43,28 @@ PROBLEMS = {
     "cartpole": (CartpoleDynamicsModel, CartpoleCost, O.cartpole_spec, [0.0, 0.0, 0.0, 0.0], 10.0),
     "double_cartpole": (DoubleCartpoleDynamicsModel, DoubleCartpoleCost, O.double_cartpole_spec,
                         [0.0, 0.0, np.pi, 0.0, np.pi, 0.0], 20.0),
+    # initial state of RendezvousEnv.reset (ref: examples/rendezvous/env.py:106-108); action_size 4
+    "rendezvous": (RendezvousDynamicsModel, lambda: rendezvous_cost_nd(), O.rendezvous_spec,
+                   [-10.0, -10.0, 10.0, 10.0, 0.0, -5.0, 5.0, 0.0], 1.0),
 }
+
+
+def rendezvous_cost_nd():
+    """The reference's QRCost with RendezvousCost's Q and a NON-DEGENERATE R.  With the stock
+    R = 0.1 I the symmetric problem makes Q_uu a multiple of the identity up to rounding; LAPACK's
+    geev (Tensor.eig, ilqr.py:631) then returns non-orthogonal eigenvectors for the repeated
+    eigenvalue and the reference's (E/e) E^T is a rounding-dependent matrix, not the regularised
+    inverse -- nothing can be pinned on it.  Distinct eigenvalues make the reference well defined."""
+    from pddp.costs import QRCost
+    R = torch.diag(torch.tensor([0.1, 0.15, 0.2, 0.3])) + 0.02 * (torch.ones(4, 4) - torch.eye(4))
+    return QRCost(RendezvousCost().Q.data.clone(), R)
 
 
 def cost_spec(cost, model_cls, dtype):
     """Reference cost object -> oracle QRCostSpec (constants read from the object's buffers)."""
+    DA = cost.Q.shape[0]
     return O.QRCostSpec(cost.Q.data.clone(), cost.R.data.clone(), cost.Q_term.data.clone(),
-                        cost.x_goal.data.clone(), cost.u_goal.data.clone().reshape(-1).expand(
+                        cost.x_goal.data.clone().reshape(-1).expand(DA).clone(), cost.u_goal.data.clone().reshape(-1).expand(
                             model_cls.action_size).clone(),
                         model_cls.state_size, tuple(model_cls.angular_indices.tolist()),
                         tuple(model_cls.non_angular_indices.tolist())).to(dtype)
@@ -124,8 +141,8 @@ def run_case(tag, name, enc, dtype, N, seed, bnn=None, bounded=False, reg=1.0, n
     U = (0.1 * torch.randn(N, model_cls.action_size)).to(dtype)
     if bounded:
         U = U * 30 * umax / 10          # make some of the nominal controls hit the bounds
-    u_min = torch.tensor([-umax], dtype=dtype) if bounded else None
-    u_max = torch.tensor([umax], dtype=dtype) if bounded else None
+    u_min = torch.full((model_cls.action_size,), -umax, dtype=dtype) if bounded else None
+    u_max = torch.full((model_cls.action_size,), umax, dtype=dtype) if bounded else None
     if bnn is not None:
         with torch.no_grad():
             model(z0, U[0], 0, enc, **model_opts)      # draws eps_in[0] and the dropout masks
@@ -170,7 +187,7 @@ def run_case(tag, name, enc, dtype, N, seed, bnn=None, bounded=False, reg=1.0, n
 
     fx = dict(name=name, enc=enc, N=N, dt=DT, reg=reg, bounded=bounded, z0=z0, U=U, alphas=alphas,
               k=k, K=K, Z_new=Zb, U_new=Ub, J=Jb, Q=cost.Q.data, R=cost.R.data,
-              Q_term=cost.Q_term.data, x_goal=cost.x_goal.data)
+              Q_term=cost.Q_term.data, x_goal=cost.x_goal.data.reshape(-1).expand(cost.Q.shape[0]))
     if bounded:
         fx.update(u_min=u_min, u_max=u_max)
     fx.update({n: v for n, v in zip(NAMES, lin)})
@@ -254,6 +271,13 @@ def main():
                    bnn=([32, 32], 12, 0.05))
     ok &= run_case("bnn_cartpole_std_small_f64", "cartpole", E.STANDARD_DEVIATION_ONLY, f64, 5, 32,
                    bnn=([32, 32], 12, 0.05))
+    # action_size 4: eigen-clipped Q_uu and the 4-dimensional box QP (the unbounded
+    # rendezvous cases come from the loops over PROBLEMS above)
+    ok &= run_case("known_rendezvous_ign_bounded_f64", "rendezvous", E.IGNORE_UNCERTAINTY, f64, 15, 42,
+                   bounded=True, fit_iters=5)
+    ok &= run_case("known_rendezvous_ut_bounded_f64", "rendezvous", E.UPPER_TRIANGULAR_CHOLESKY, f64, 8, 43,
+                   bounded=True)
+    ok &= run_case("known_rendezvous_ign_f32", "rendezvous", E.IGNORE_UNCERTAINTY, f32, 30, 44)
     # BNN input-particle options: infer_noise_variables=False, sample_input_distribution=False
     ok &= run_case("bnn_cartpole_ut_resample_small_f64", "cartpole", E.UPPER_TRIANGULAR_CHOLESKY, f64, 5,
                    33, bnn=([32, 32], 12, 0.05), input_mode="resample")

@@ -370,12 +370,29 @@ def _double_cartpole(p, x, u):
     return torch.stack([pos + nvel * dt, nvel, t1 + n1 * dt, n1, t2 + n2 * dt, n2], -1)
 
 
-_KNOWN = {"pendulum": _pendulum, "cartpole": _cartpole, "double_cartpole": _double_cartpole}
+def rendezvous_spec(dt, m=1.0, alpha=0.1):
+    return KnownDynamicsSpec("rendezvous", dict(dt=dt, m=m, alpha=alpha), 8, 4, (), tuple(range(8)))
+
+
+def _rendezvous(p, x, u):
+    """ref: examples/rendezvous/model.py:79-115 -- two point masses with friction; the reference's
+    `_acceleration` returns v (1 - alpha dt / m) + u dt / m and the step adds it times dt."""
+    dt, m, al = p["dt"], p["m"], p["alpha"]
+    pos, vel = x[..., :4], x[..., 4:]
+    acc = vel * (1 - al * dt / m) + u * dt / m
+    return torch.cat([pos + vel * dt, vel + acc * dt], -1)
+
+
+_KNOWN = {"pendulum": _pendulum, "cartpole": _cartpole, "double_cartpole": _double_cartpole,
+          "rendezvous": _rendezvous}
 
 
 def known_step(spec, z, u, enc, carry=None, i=None):
-    """Mean through the ODE step, variance passed through unchanged."""
+    """Mean through the ODE step, variance passed through unchanged; the
+    rendezvous model passes the whole covariance through (ref: rendezvous/model.py:98,112)."""
     mean = _KNOWN[spec.kind](spec.params, decode_mean(z, enc, spec.D), u)
+    if spec.kind == "rendezvous":
+        return encode(mean, C=decode_covar(z, enc, spec.D), enc=enc), None
     return encode(mean, V=decode_var(z, enc, spec.D), enc=enc), None
 
 

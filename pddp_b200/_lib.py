@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpddp_b200.so")
 F32, F64 = 0, 1
 PROBLEM_MAJOR, BATCH_INNER = 0, 1
 GEO_PENDULUM, GEO_CARTPOLE, GEO_DOUBLE_CARTPOLE = 0, 1, 2
-MAX_DA, MAX_NU = 8, 1
+MAX_DA, MAX_NU = 8, 4
 STATUS_NOT_PD, STATUS_NAN = 1, 2
 BNN_INPUT_INFER, BNN_INPUT_RESAMPLE, BNN_INPUT_MEAN = 0, 1, 2
 

@@ -306,15 +306,10 @@ class _RawBackward:
     """pddp_backward on caller tensors (B = 1): only shapes matter, not the model."""
 
     def __init__(self, nz, nu, N, dtype, device):
-        geo_enc = None
-        for geo, (D, _, _, _) in _lib.GEO_INFO.items():
-            for enc in (4, 1, 0):
-                from .encoding import infer_encoded_state_size
-                if infer_encoded_state_size(D, StateEncoding(enc)) == nz:
-                    geo_enc = geo_enc or (geo, enc)
-        if geo_enc is None or nu != 1:
-            raise NotImplementedError("pddp_b200.backward: unsupported (nz=%d, nu=%d)" % (nz, nu))
-        self.shape = _lib.Shape(_lib.dtype_code(dtype), _lib.PROBLEM_MAJOR, geo_enc[0], geo_enc[1], 1, N, nz, nu)
+        if not 1 <= nu <= _lib.MAX_NU:
+            raise NotImplementedError("pddp_b200.backward: action_size must be in [1, %d], got %d" % (_lib.MAX_NU, nu))
+        # pddp_backward ignores geo / enc: the derivative tensors carry everything it needs
+        self.shape = _lib.Shape(_lib.dtype_code(dtype), _lib.PROBLEM_MAJOR, 0, 0, 1, N, nz, nu)
         self.N, self.nz, self.nu, self.dtype, self.device = N, nz, nu, dtype, device
 
     def run(self, F_z, F_u, L_z, L_u, L_zz, L_uz, L_uu, reg, U, u_min, u_max):

@@ -12,6 +12,7 @@
 // Roofline: HBM -- per trajectory-step 2nz^2+2nz*nu+nz+nu+nu^2 elements read, nu+nu*nz written.
 #include "core.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace pddp {
 
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(128, (sizeof(T) == 4 && NZ <= 2) ? 5 : 2) back
 //               time loop is a chain of LDS->FMA latencies, 8 warps split every product 8 ways).
 template <int TEAM>
 __device__ __forceinline__ void team_sync() {
-    if (TEAM == 32) team_sync<TEAM>(); else __syncthreads();
+    if (TEAM == 32) __syncwarp(); else __syncthreads();
 }
 template <int TEAM>
 __device__ __forceinline__ bool team_any(bool x) {
@@ -356,6 +357,11 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(
 
 template <class T>
 cudaError_t backward_pass(const BackwardArgs<T>& a, int layout, cudaStream_t s) {
+    // action_size > 1 (eigen-clipping by Jacobi rotations, n-dimensional box QP): backward_nu.cu.
+    // PDDP_FORCE_BACKWARD_NU=1 sends nu == 1 there too (tests compare the two kernels).
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("PDDP_FORCE_BACKWARD_NU"); forced = (e && e[0] == '1') ? 1 : 0; }
+    if (a.nu > 1 || forced) return backward_pass_nu<T>(a, s);
     const int threads = 128;
     if (layout == LAYOUT_BATCH_INNER && (a.nz == 2 || a.nz == 4)) {
         const int grid = (a.B + threads - 1) / threads;

@@ -580,8 +580,8 @@ static void fill_cost_params(const pddp_cost* c, int DA, CostParams<T>& out) {
     memset(&out, 0, sizeof(out));
     for (int i = 0; i < DA * DA; ++i) { out.Q[i] = (T)c->Q[i]; out.Qt[i] = (T)c->Q_term[i]; }
     for (int i = 0; i < DA; ++i) out.xg[i] = (T)c->x_goal[i];
-    out.R[0] = (T)c->R[0];
-    out.ug[0] = (T)c->u_goal[0];
+    for (int i = 0; i < MAX_NU * MAX_NU; ++i) out.R[i] = (T)c->R[i];
+    for (int i = 0; i < MAX_NU; ++i) out.ug[i] = (T)c->u_goal[i];
 }
 
 #define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return e__; } while (0)

@@ -40,8 +40,19 @@ static void fill_cost(const pddp_cost* c, int DA, CostParams<T>& out) {
     memset(&out, 0, sizeof(out));
     for (int i = 0; i < DA * DA; ++i) { out.Q[i] = (T)c->Q[i]; out.Qt[i] = (T)c->Q_term[i]; }
     for (int i = 0; i < DA; ++i) out.xg[i] = (T)c->x_goal[i];
-    out.R[0] = (T)c->R[0];
-    out.ug[0] = (T)c->u_goal[0];
+    for (int i = 0; i < MAX_NU * MAX_NU; ++i) out.R[i] = (T)c->R[i];
+    for (int i = 0; i < MAX_NU; ++i) out.ug[i] = (T)c->u_goal[i];
+}
+
+// pddp_backward only sees derivative tensors: no geometry / encoding constraints
+static int check_shape_backward(const pddp_shape* s) {
+    if (!s) return fail(PDDP_E_BADARG, "shape is NULL");
+    if (s->dtype != PDDP_F32 && s->dtype != PDDP_F64) return fail(PDDP_E_BADARG, "dtype must be PDDP_F32 or PDDP_F64");
+    if (s->layout != PDDP_PROBLEM_MAJOR && s->layout != PDDP_BATCH_INNER) return fail(PDDP_E_BADARG, "bad layout");
+    if (s->nu < 1 || s->nu > PDDP_MAX_NU) return fail(PDDP_E_UNSUPPORTED, "pddp_backward: 1 <= action_size <= PDDP_MAX_NU");
+    if (s->nz < 1 || s->nz > 96) return fail(PDDP_E_UNSUPPORTED, "pddp_backward: 1 <= nz <= 96");
+    if (s->B < 1 || s->N < 1) return fail(PDDP_E_BADARG, "B and N must be positive");
+    return 0;
 }
 
 int pddp_capi_fail(int code, const char* msg) { return fail(code, msg); }
@@ -108,7 +119,7 @@ static int backward_t(const pddp_shape* s, const void* F_z, const void* F_u, con
                       const void* u_min, const void* u_max, const int32_t* active, void* k, void* K,
                       int32_t* status, cudaStream_t st) {
     BackwardArgs<T> a;
-    a.B = s->B; a.N = s->N; a.nz = s->nz;
+    a.B = s->B; a.N = s->N; a.nz = s->nz; a.nu = s->nu;
     a.F_z = (const T*)F_z; a.F_u = (const T*)F_u; a.L_z = (const T*)L_z; a.L_u = (const T*)L_u;
     a.L_zz = (const T*)L_zz; a.L_uz = (const T*)L_uz; a.L_uu = (const T*)L_uu; a.mu = mu;
     a.U = (const T*)U; a.u_min = (const T*)u_min; a.u_max = (const T*)u_max; a.active = active;
@@ -127,7 +138,7 @@ extern "C" int pddp_backward(const pddp_shape* s, const void* F_z, const void* F
                              const void* L_u, const void* L_zz, const void* L_uz, const void* L_uu,
                              const double* mu, const void* U, const void* u_min, const void* u_max,
                              const int32_t* active, void* k, void* K, int32_t* status, void* stream) {
-    if (int e = check_shape(s)) return e;
+    if (int e = check_shape_backward(s)) return e;
     if (!F_z || !F_u || !L_z || !L_u || !L_zz || !L_uz || !L_uu || !mu || !k || !K || !status)
         return fail(PDDP_E_BADARG, "pddp_backward: NULL argument");
     if ((u_min == nullptr) != (u_max == nullptr)) return fail(PDDP_E_BADARG, "u_min and u_max must be given together");

@@ -16,7 +16,7 @@ enum { ST_UNDEFINED = 0, ST_ACCEPTED = 1, ST_REJECTED = 2, ST_NOT_PD = 3, ST_MAX
 enum { LAYOUT_PROBLEM_MAJOR = 0, LAYOUT_BATCH_INNER = 1 };
 
 constexpr int MAX_DA = 8;
-constexpr int MAX_NU = 1;   // general nu is SURVEY 8(f) "next"
+constexpr int MAX_NU = 4;   // rendezvous (ref: examples/rendezvous/model.py) has action_size 4
 
 // ---- geometry: which state dims are angles (ref: examples/*/model.py angular_indices) -------
 template <int GEO> struct Geo;

@@ -29,7 +29,7 @@ struct RollKnownArgs {
 
 template <class T>
 struct BackwardArgs {
-    int B, N, nz;
+    int B, N, nz, nu;
     const T* F_z; const T* F_u; const T* L_z; const T* L_u; const T* L_zz; const T* L_uz; const T* L_uu;
     const double* mu; const T* U; const T* u_min; const T* u_max; const int32_t* active;
     T* k; T* K; int32_t* status;
@@ -58,6 +58,7 @@ struct CostDerivArgs {
 template <class T> cudaError_t linearize_known(int geo, int enc, const LinKnownArgs<T>&, cudaStream_t);
 template <class T> cudaError_t rollout_known(int geo, int enc, const RollKnownArgs<T>&, cudaStream_t);
 template <class T> cudaError_t backward_pass(const BackwardArgs<T>&, int layout, cudaStream_t);
+template <class T> cudaError_t backward_pass_nu(const BackwardArgs<T>&, cudaStream_t);      // backward_nu.cu, nu <= MAX_NU
 template <class T> cudaError_t accept_update(const AcceptArgs<T>&, int32_t* accepted_scratch, cudaStream_t);
 template <class T> cudaError_t cost_derivatives(int geo, int enc, const CostDerivArgs<T>&, cudaStream_t);
 

@@ -14,9 +14,10 @@ GEOMETRY = {  # name -> (D, nu, angular, non-angular)
     "pendulum": (2, 1, (0,), (1,)),
     "cartpole": (4, 1, (2,), (0, 1, 3)),
     "double_cartpole": (6, 1, (2, 4), (0, 1, 3, 5)),
+    "rendezvous": (8, 4, (), tuple(range(8))),
 }
 SPEC_FN = {"pendulum": O.pendulum_spec, "cartpole": O.cartpole_spec,
-           "double_cartpole": O.double_cartpole_spec}
+           "double_cartpole": O.double_cartpole_spec, "rendezvous": O.rendezvous_spec}
 
 
 def all_tags():

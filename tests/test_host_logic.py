@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts():
     assert ctypes.sizeof(_lib.Shape) == 8 * 4
-    assert ctypes.sizeof(_lib.Cost) == (64 + 64 + 1 + 8 + 1) * 8
+    assert ctypes.sizeof(_lib.Cost) == (64 + 64 + 16 + 8 + 4) * 8
     assert ctypes.sizeof(_lib.KnownDynamics) == 64
     assert ctypes.sizeof(_lib.BNN) == 16 + 13 * 8 + 8 + 8     # + input_mode (padded) + eps_in
 

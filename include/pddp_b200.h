@@ -45,6 +45,7 @@ extern "C" {
 #define PDDP_GEO_PENDULUM 0        /* D=2, angles {0}      */
 #define PDDP_GEO_CARTPOLE 1        /* D=4, angles {2}      */
 #define PDDP_GEO_DOUBLE_CARTPOLE 2 /* D=6, angles {2,4}    */
+#define PDDP_GEO_RENDEZVOUS 3      /* D=8, no angles, action_size 4 (pddp/examples/rendezvous/model.py; known dynamics only) */
 
 /* pddp/controllers/ilqr.py:35-64 (iLQRState) */
 #define PDDP_STATE_UNDEFINED 0
@@ -82,13 +83,13 @@ typedef struct pddp_shape {
 typedef struct pddp_cost {
     double Q[PDDP_MAX_DA * PDDP_MAX_DA];
     double Q_term[PDDP_MAX_DA * PDDP_MAX_DA];
-    double R[PDDP_MAX_NU * PDDP_MAX_NU];
+    double R[PDDP_MAX_NU * PDDP_MAX_NU];   /* row-major nu x nu (stride nu) */
     double x_goal[PDDP_MAX_DA];
     double u_goal[PDDP_MAX_NU];
 } pddp_cost;
 
 /* Known-dynamics constants (host memory). p[] = pendulum: dt,m,l,mu,g ; cartpole: dt,mc,mp,l,mu,g ;
- * double cartpole: dt,mc,mp1,mp2,l1,l2,mu,g.
+ * double cartpole: dt,mc,mp1,mp2,l1,l2,mu,g ; rendezvous: dt,m,alpha.
  * Replaces: pddp/examples/<problem>/model.py constructor Parameters. */
 typedef struct pddp_known_dynamics {
     double p[8];

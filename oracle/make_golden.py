@@ -242,8 +242,10 @@ def main():
     for name in PROBLEMS:
         for enc, etag in ((E.IGNORE_UNCERTAINTY, "ign"), (E.UPPER_TRIANGULAR_CHOLESKY, "ut"),
                           (E.FULL_COVARIANCE_MATRIX, "full")):
+            # (rendezvous is linear-quadratic: one Newton step lands on the optimum, and whether a second
+            # iteration is ACCEPTED or REJECTED there is a rounding coin flip -- one iteration only)
             ok &= run_case("known_%s_%s_f64" % (name, etag), name, enc, f64, 12, 11,
-                           fit_iters=4 if enc == E.IGNORE_UNCERTAINTY else 0)
+                           fit_iters=0 if enc != E.IGNORE_UNCERTAINTY else 1 if name == "rendezvous" else 4)
     ok &= run_case("known_pendulum_ign_f32", "pendulum", E.IGNORE_UNCERTAINTY, f32, 100, 3,
                    fit_iters=6)
     ok &= run_case("known_pendulum_ign_bounded_f64", "pendulum", E.IGNORE_UNCERTAINTY, f64, 20, 5,

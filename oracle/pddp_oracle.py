@@ -618,7 +618,7 @@ def boxqp(x0, Q, c, lower, upper, max_iter=100, min_grad=1e-8, tol=1e-8, step_de
 
 
 def backward_pass(Z, F_z, F_u, L, L_z, L_u, L_zz, L_uz, L_uu, reg=0.0, u_min=None, u_max=None,
-                  U=None):
+                  U=None, symmetric_eig=False):
     """ref: controllers/ilqr.py:626-672.  Eigen-clip Q_uu (e<0 -> 1e-12), add reg; gains from the
     regularised inverse, value update with the UN-regularised Q_uu.  Raises NotPositiveDefinite
     where the reference raises RuntimeError."""
@@ -632,8 +632,16 @@ def backward_pass(Z, F_z, F_u, L, L_z, L_u, L_zz, L_uz, L_uu, reg=0.0, u_min=Non
                                              L_uu[t], V_z, V_zz)
         if not torch.isfinite(Q_uu).all():
             raise NotPositiveDefinite("Q_uu has NaN/Inf")   # torch.linalg.eig raises (shim)
-        w, E = torch.linalg.eig(Q_uu)
-        e, E = w.real.clone(), E.real
+        if symmetric_eig:
+            # orthonormal eigenvectors.  The reference's general `eig` (LAPACK geev) returns
+            # non-orthogonal vectors for a REPEATED eigenvalue, and (E/e)E^T is then a rounding-
+            # dependent matrix instead of the regularised inverse (stock RendezvousCost: Q_uu is a
+            # multiple of I).  Where the eigenvalues are distinct the two agree.
+            e, E = torch.linalg.eigh(Q_uu)
+            e = e.clone()
+        else:
+            w, E = torch.linalg.eig(Q_uu)
+            e, E = w.real.clone(), E.real
         e[e < 0] = 1e-12
         e = e + reg
         if u_min is None or u_max is None:

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpddp_b200.so")
 
 F32, F64 = 0, 1
 PROBLEM_MAJOR, BATCH_INNER = 0, 1
-GEO_PENDULUM, GEO_CARTPOLE, GEO_DOUBLE_CARTPOLE = 0, 1, 2
+GEO_PENDULUM, GEO_CARTPOLE, GEO_DOUBLE_CARTPOLE, GEO_RENDEZVOUS = 0, 1, 2, 3
 MAX_DA, MAX_NU = 8, 4
 STATUS_NOT_PD, STATUS_NAN = 1, 2
 BNN_INPUT_INFER, BNN_INPUT_RESAMPLE, BNN_INPUT_MEAN = 0, 1, 2
@@ -20,6 +20,7 @@ GEO_INFO = {  # geo -> (D, nu, angular, non-angular)
     GEO_PENDULUM: (2, 1, (0,), (1,)),
     GEO_CARTPOLE: (4, 1, (2,), (0, 1, 3)),
     GEO_DOUBLE_CARTPOLE: (6, 1, (2, 4), (0, 1, 3, 5)),
+    GEO_RENDEZVOUS: (8, 4, (), tuple(range(8))),       # known dynamics only (ref: examples/rendezvous)
 }
 
 

@@ -339,7 +339,8 @@ def _control_law(model, Z, U, k, K, alpha, encoding=StateEncoding.DEFAULT, model
     from .costs import QRCost
     u_min, u_max = _bounds(u_min, u_max)
     DA = model.state_size + len(model.angular_indices)
-    cost = cost or QRCost(torch.zeros(DA, DA), torch.zeros(1, 1), state_size=model.state_size,
+    cost = cost or QRCost(torch.zeros(DA, DA), torch.zeros(int(model.action_size), int(model.action_size)),
+                          state_size=model.state_size,
                           angular_indices=model.angular_indices.tolist())
     s = _solver_for(model, cost, encoding, 1, U.shape[0], U.dtype, U.device, model_opts=model_opts)
     Zs, Us = [], []

@@ -61,7 +61,7 @@ class QRCost(Cost):
         geo = self.geometry()
         s = BatchedSolver(KnownDynamics(geo, [0.0] * 8), self.constants(), encoding, B, 1, dtype=zz.dtype,
                           device=zz.device, layout=_lib.PROBLEM_MAJOR)
-        uu = torch.zeros(B, 1, 1, dtype=zz.dtype, device=zz.device) if u is None else u.reshape(B, 1, -1)
+        uu = torch.zeros(B, 1, self.R.shape[0], dtype=zz.dtype, device=zz.device) if u is None else u.reshape(B, 1, -1)
         Z = zz.unsqueeze(1).expand(B, 2, -1)
         s.store("Z", Z)
         s.store("U", uu)
@@ -99,6 +99,16 @@ class CartpoleCost(QRCost):
         Q[3, 3] = Q[4, 4] = l ** 2
         super().__init__(Q, 0.1 * torch.eye(1), torch.eye(5), _augmented_goal([0.0, 0.0, math.pi, 0.0], (2,)),
                          state_size=4, angular_indices=(2,))
+
+
+class RendezvousCost(QRCost):
+    """ref: pddp/examples/rendezvous/cost.py:29-43 (||x_0 - x_1||^2 + velocities, R = 0.1 I, Q_term = Q)"""
+
+    def __init__(self):
+        Q = torch.eye(8)
+        Q[0, 2] = Q[2, 0] = -1
+        Q[1, 3] = Q[3, 1] = -1
+        super().__init__(Q, 0.1 * torch.eye(4), state_size=8, angular_indices=())
 
 
 class DoubleCartpoleCost(QRCost):

@@ -760,6 +760,7 @@ int pddp_capi_check_shape(const pddp_shape* s);         // capi.cu
 static int check_bnn(const pddp_shape* s, const pddp_bnn* n) {
     if (int e = pddp_capi_check_shape(s)) return e;
     if (s->layout != PDDP_PROBLEM_MAJOR) return pddp_capi_fail(PDDP_E_UNSUPPORTED, "BNN path uses PDDP_PROBLEM_MAJOR");
+    if (s->geo > GEO_DOUBLE_CARTPOLE) return pddp_capi_fail(PDDP_E_UNSUPPORTED, "BNN kernels exist for the pendulum, cartpole and double-cartpole geometries (action_size 1)");
     if (!n) return pddp_capi_fail(PDDP_E_BADARG, "bnn is NULL");
     if (n->P < 2 || n->P > 1024) return pddp_capi_fail(PDDP_E_BADARG, "2 <= particles <= 1024");
     if (n->H0 < 1 || n->H1 < 1 || n->H0 > 256 || n->H1 > 256) return pddp_capi_fail(PDDP_E_UNSUPPORTED, "hidden widths must be in [1,256]");

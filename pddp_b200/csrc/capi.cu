@@ -20,16 +20,17 @@ static int cuda_result(cudaError_t e, const char* what) {
     return (int)e;
 }
 
-static int geo_D(int geo) { return geo == GEO_PENDULUM ? 2 : geo == GEO_CARTPOLE ? 4 : geo == GEO_DOUBLE_CARTPOLE ? 6 : -1; }
+static int geo_D(int geo) { return geo == GEO_PENDULUM ? 2 : geo == GEO_CARTPOLE ? 4 : geo == GEO_DOUBLE_CARTPOLE ? 6 : geo == GEO_RENDEZVOUS ? 8 : -1; }
 static int geo_DA(int geo) { return geo == GEO_PENDULUM ? 3 : geo == GEO_CARTPOLE ? 5 : 8; }
+static int geo_nu(int geo) { return geo == GEO_RENDEZVOUS ? 4 : 1; }
 
 static int check_shape(const pddp_shape* s) {
     if (!s) return fail(PDDP_E_BADARG, "shape is NULL");
     if (s->dtype != PDDP_F32 && s->dtype != PDDP_F64) return fail(PDDP_E_BADARG, "dtype must be PDDP_F32 or PDDP_F64");
     if (s->layout != PDDP_PROBLEM_MAJOR && s->layout != PDDP_BATCH_INNER) return fail(PDDP_E_BADARG, "bad layout");
-    if (geo_D(s->geo) < 0) return fail(PDDP_E_UNSUPPORTED, "unsupported geometry (pendulum, cartpole, double_cartpole)");
+    if (geo_D(s->geo) < 0) return fail(PDDP_E_UNSUPPORTED, "unsupported geometry (pendulum, cartpole, double_cartpole, rendezvous)");
     if (s->enc < 0 || s->enc > 4) return fail(PDDP_E_BADARG, "bad encoding");
-    if (s->nu != 1) return fail(PDDP_E_UNSUPPORTED, "only action_size == 1 is implemented (general nu: SURVEY 8f)");
+    if (s->nu != geo_nu(s->geo)) return fail(PDDP_E_BADARG, "nu does not match the geometry's action size");
     if (s->nz != enc_size(geo_D(s->geo), s->enc)) return fail(PDDP_E_BADARG, "nz does not match the encoding size of this geometry");
     if (s->B < 1 || s->N < 1) return fail(PDDP_E_BADARG, "B and N must be positive");
     return 0;
@@ -86,6 +87,11 @@ static int linearize_known_t(const pddp_shape* s, const pddp_known_dynamics* dyn
     // uncertain encodings: the kernel rolls the nominal trajectory + dynamics Jacobians and parks
     // the clamped controls in the L_u buffer; the pair-parallel cost kernel then reads them back
     // (the only thread that reads U[b,t] is the one that overwrites L_u[b,t]).
+    if (s->geo == GEO_RENDEZVOUS) {             // linear-quadratic: dynamics and cost derivatives in one kernel
+        a.U_clamped = nullptr;
+        note_launches(1);
+        return cuda_result(linearize_lq<T>(s->enc, a, st), "pddp_linearize_known(rendezvous)");
+    }
     a.U_clamped = s->enc == PDDP_ENC_IGNORE_UNCERTAINTY ? nullptr : (T*)L_u;
     if (int e = cuda_result(linearize_known<T>(s->geo, s->enc, a, st), "pddp_linearize_known")) return e;
     note_launches(s->enc == PDDP_ENC_IGNORE_UNCERTAINTY ? 1 : 3);
@@ -167,6 +173,7 @@ static int rollout_known_t(const pddp_shape* s, const pddp_known_dynamics* dyn, 
     a.lZ = make_layout(ly, B, N + 1, nz); a.lU = make_layout(ly, B, N, nu);
     a.lk = make_layout(ly, B, N, nu); a.lK = make_layout(ly, B, N, nu * nz);
     note_launches(2);
+    if (s->geo == GEO_RENDEZVOUS) return cuda_result(rollout_lq<T>(s->enc, a, st), "pddp_rollout_known(rendezvous)");
     return cuda_result(rollout_known<T>(s->geo, s->enc, a, st), "pddp_rollout_known");
 }
 
@@ -233,6 +240,10 @@ static int cost_derivs_t(const pddp_shape* s, const pddp_cost* cost, const void*
     a.lL = make_layout(ly, B, N + 1, 1); a.lLz = make_layout(ly, B, N + 1, nz);
     a.lLu = make_layout(ly, B, N, nu); a.lLzz = make_layout(ly, B, N + 1, nz * nz);
     a.lLuz = make_layout(ly, B, N, nu * nz); a.lLuu = make_layout(ly, B, N, nu * nu);
+    if (s->geo == GEO_RENDEZVOUS) {
+        note_launches(a.J_opt ? 2 : 1);
+        return cuda_result(cost_derivatives_lq<T>(s->enc, a, st), "pddp_cost_derivatives(rendezvous)");
+    }
     note_launches((a.J_opt ? 2 : 1) + (s->enc == PDDP_ENC_FULL_COVARIANCE_MATRIX ? 1 : 0));
     return cuda_result(cost_derivatives<T>(s->geo, s->enc, a, st), "pddp_cost_derivatives");
 }

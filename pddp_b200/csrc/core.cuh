@@ -10,7 +10,7 @@ namespace pddp {
 
 // ---- enums shared with include/pddp_b200.h -------------------------------------------------
 enum { ENC_FULL = 0, ENC_UT = 1, ENC_VAR = 2, ENC_STD = 3, ENC_IGNORE = 4 };      // ref: utils/encoding.py:25-33
-enum { GEO_PENDULUM = 0, GEO_CARTPOLE = 1, GEO_DOUBLE_CARTPOLE = 2 };
+enum { GEO_PENDULUM = 0, GEO_CARTPOLE = 1, GEO_DOUBLE_CARTPOLE = 2, GEO_RENDEZVOUS = 3 };   // 3: known_lq.cu
 enum { ST_UNDEFINED = 0, ST_ACCEPTED = 1, ST_REJECTED = 2, ST_NOT_PD = 3, ST_MAX_REG = 4,
        ST_CONVERGED = 5 };                                                       // ref: controllers/ilqr.py:35-64
 enum { LAYOUT_PROBLEM_MAJOR = 0, LAYOUT_BATCH_INNER = 1 };

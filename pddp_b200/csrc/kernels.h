@@ -57,6 +57,9 @@ struct CostDerivArgs {
 
 template <class T> cudaError_t linearize_known(int geo, int enc, const LinKnownArgs<T>&, cudaStream_t);
 template <class T> cudaError_t rollout_known(int geo, int enc, const RollKnownArgs<T>&, cudaStream_t);
+template <class T> cudaError_t linearize_lq(int enc, const LinKnownArgs<T>&, cudaStream_t);      // known_lq.cu (rendezvous)
+template <class T> cudaError_t rollout_lq(int enc, const RollKnownArgs<T>&, cudaStream_t);
+template <class T> cudaError_t cost_derivatives_lq(int enc, const CostDerivArgs<T>&, cudaStream_t);
 template <class T> cudaError_t backward_pass(const BackwardArgs<T>&, int layout, cudaStream_t);
 template <class T> cudaError_t backward_pass_nu(const BackwardArgs<T>&, cudaStream_t);      // backward_nu.cu, nu <= MAX_NU
 template <class T> cudaError_t accept_update(const AcceptArgs<T>&, int32_t* accepted_scratch, cudaStream_t);

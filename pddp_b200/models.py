@@ -22,8 +22,9 @@ def geometry_of(state_size, angular_indices):
     for geo, (D, _, a, _) in _lib.GEO_INFO.items():
         if D == state_size and a == ang:
             return geo
-    raise NotImplementedError("pddp_b200 has kernels for the pendulum (D=2, angle 0), cartpole (D=4, angle 2) and "
-                              "double-cartpole (D=6, angles 2,4) state geometries; got D=%d angles=%s" % (state_size, ang))
+    raise NotImplementedError("pddp_b200 has kernels for the pendulum (D=2, angle 0), cartpole (D=4, angle 2), "
+                              "double-cartpole (D=6, angles 2,4) and rendezvous (D=8, no angles) state geometries; "
+                              "got D=%d angles=%s" % (state_size, ang))
 
 
 class DynamicsModel(torch.nn.Module):
@@ -52,7 +53,8 @@ class DynamicsModel(torch.nn.Module):
             raise NotImplementedError("pddp_b200: a stand-alone BNN forward is only defined for step 0 (particles "
                                       "drawn from eps_in[0]); later steps depend on the particle cache that the "
                                       "controller's rollout carries on the device")
-        dummy = QRCostConstants(torch.zeros(_DA(self), _DA(self)), torch.zeros(1, 1), torch.zeros(_DA(self), _DA(self)),
+        nu = int(self.action_size)
+        dummy = QRCostConstants(torch.zeros(_DA(self), _DA(self)), torch.zeros(nu, nu), torch.zeros(_DA(self), _DA(self)),
                                 torch.zeros(_DA(self)))
         s = BatchedSolver(self.descriptor(), dummy, encoding, zz.shape[0], 1, dtype=zz.dtype, device=zz.device)
         s.set_problem(zz, uu.unsqueeze(1), alphas=torch.ones(1))
@@ -75,7 +77,7 @@ class _KnownModel(DynamicsModel):
 
     def descriptor(self):
         geo = geometry_of(self.state_size, self.angular_indices.tolist())
-        return KnownDynamics(geo, [float(getattr(self, n)) for n in self._param_order])
+        return KnownDynamics(geo, [float(getattr(self, n).detach()) for n in self._param_order])
 
 
 class PendulumDynamicsModel(_KnownModel):
@@ -117,6 +119,22 @@ class DoubleCartpoleDynamicsModel(_KnownModel):
         super().__init__()
         self.dt = Parameter(torch.tensor(dt), requires_grad=False)
         for n, v in (("mc", mc), ("mp1", mp1), ("mp2", mp2), ("l1", l1), ("l2", l2), ("mu", mu), ("g", g)):
+            setattr(self, n, Parameter(torch.tensor(v), requires_grad=True))
+
+
+class RendezvousDynamicsModel(_KnownModel):
+    """ref: pddp/examples/rendezvous/model.py:25-115 (state [x0, y0, x1, y1, and their velocities],
+    action [Fx0, Fy0, Fx1, Fy1]; linear dynamics, the whole covariance is passed through)."""
+    state_size = 8
+    action_size = 4
+    angular_indices = torch.tensor([]).long()
+    non_angular_indices = torch.arange(8).long()
+    _param_order = ("dt", "m", "alpha")
+
+    def __init__(self, dt, m=1.0, alpha=0.1):
+        super().__init__()
+        self.dt = Parameter(torch.tensor(dt), requires_grad=False)
+        for n, v in (("m", m), ("alpha", alpha)):
             setattr(self, n, Parameter(torch.tensor(v), requires_grad=True))
 
 

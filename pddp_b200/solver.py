@@ -105,8 +105,9 @@ class QRCostConstants:
         DA = self.Q.shape[0]
         if DA > _lib.MAX_DA or self.Q.shape != (DA, DA) or self.Q_term.shape != (DA, DA):
             raise ValueError("Q / Q_term must be square, at most %dx%d" % (_lib.MAX_DA, _lib.MAX_DA))
-        if self.R.numel() != 1:
-            raise NotImplementedError("pddp_b200: only action_size == 1 is implemented")
+        nu = int(round(self.R.numel() ** 0.5))
+        if nu * nu != self.R.numel() or nu > _lib.MAX_NU or self.u_goal.numel() not in (1, nu):
+            raise ValueError("R must be nu x nu with nu <= %d, u_goal a scalar or [nu]" % _lib.MAX_NU)
         s = _lib.Cost()
         for i, v in enumerate(self.Q.reshape(-1).tolist()):
             s.Q[i] = v
@@ -114,8 +115,10 @@ class QRCostConstants:
             s.Q_term[i] = v
         for i, v in enumerate(self.x_goal.tolist()):
             s.x_goal[i] = v
-        s.R[0] = float(self.R[0])
-        s.u_goal[0] = float(self.u_goal.reshape(-1)[0])
+        for i, v in enumerate(self.R.tolist()):          # row-major nu x nu
+            s.R[i] = v
+        for i, v in enumerate(self.u_goal.reshape(-1).expand(nu).tolist()):
+            s.u_goal[i] = v
         return s
 
 

@@ -6,10 +6,11 @@ from pddp_b200 import _lib
 from pddp_b200.solver import BatchedSolver, KnownDynamics, QRCostConstants
 
 GEO = {"pendulum": _lib.GEO_PENDULUM, "cartpole": _lib.GEO_CARTPOLE,
-       "double_cartpole": _lib.GEO_DOUBLE_CARTPOLE}
+       "double_cartpole": _lib.GEO_DOUBLE_CARTPOLE, "rendezvous": _lib.GEO_RENDEZVOUS}
 PARAM_ORDER = {"pendulum": ("dt", "m", "l", "mu", "g"),
                "cartpole": ("dt", "mc", "mp", "l", "mu", "g"),
-               "double_cartpole": ("dt", "mc", "mp1", "mp2", "l1", "l2", "mu", "g")}
+               "double_cartpole": ("dt", "mc", "mp1", "mp2", "l1", "l2", "mu", "g"),
+               "rendezvous": ("dt", "m", "alpha")}
 
 
 def cost_from_fixture(fx):

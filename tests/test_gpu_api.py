@@ -12,8 +12,12 @@ pytestmark = pytest.mark.gpu
 def build(fx):
     import pddp_b200 as P
     models, costs = P.models, P.costs
-    cost = {"pendulum": costs.PendulumCost, "cartpole": costs.CartpoleCost,
-            "double_cartpole": costs.DoubleCartpoleCost}[fx.name]().to(fx.dtype)
+    if fx.name == "rendezvous":     # the fixtures use RendezvousCost's Q with a non-degenerate R (oracle/make_golden.py)
+        assert torch.equal(costs.RendezvousCost().Q.data.double(), fx.t("Q").double())
+        cost = costs.QRCost(fx.t("Q"), fx.t("R"), state_size=8, angular_indices=()).to(fx.dtype)
+    else:
+        cost = {"pendulum": costs.PendulumCost, "cartpole": costs.CartpoleCost,
+                "double_cartpole": costs.DoubleCartpoleCost}[fx.name]().to(fx.dtype)
     if fx.is_bnn:
         ang = {"cartpole": ([2], [0, 1, 3]), "double_cartpole": ([2, 4], [0, 1, 3, 5])}[fx.name]
         hidden = [int(h) for h in fx.raw["hidden"]]
@@ -32,7 +36,8 @@ def build(fx):
             opts["sample_input_distribution"] = False
     else:
         cls = {"pendulum": models.PendulumDynamicsModel, "cartpole": models.CartpoleDynamicsModel,
-               "double_cartpole": models.DoubleCartpoleDynamicsModel}[fx.name]
+               "double_cartpole": models.DoubleCartpoleDynamicsModel,
+               "rendezvous": models.RendezvousDynamicsModel}[fx.name]
         model = cls(**fx.known_params()).to(fx.dtype)
         opts = {}
     return model, cost, opts
@@ -40,7 +45,8 @@ def build(fx):
 
 TAGS = ["known_pendulum_ign_f64", "known_cartpole_ut_bounded_f64", "known_double_cartpole_full_f64",
         "bnn_cartpole_ut_small_f64", "bnn_double_cartpole_full_small_f64", "bnn_cartpole_ut_bounded_f64",
-        "bnn_cartpole_ut_resample_small_f64", "bnn_cartpole_ut_mean_small_f64"]
+        "bnn_cartpole_ut_resample_small_f64", "bnn_cartpole_ut_mean_small_f64",
+        "known_rendezvous_ign_bounded_f64", "known_rendezvous_ut_f64"]
 
 
 @pytest.mark.parametrize("tag", TAGS)
@@ -76,7 +82,8 @@ def test_backward_raises_like_the_reference():
 
 
 @pytest.mark.parametrize("tag", ["known_pendulum_ign_f64", "known_pendulum_ign_bounded_f64",
-                                 "bnn_cartpole_ut_small_f64"])
+                                 "bnn_cartpole_ut_small_f64", "known_rendezvous_ign_bounded_f64",
+                                 "known_rendezvous_ign_f64"])
 def test_controller_fit_single_problem(tag):
     """controller.fit(U) with the reference call shape: env supplies the state, callbacks fire
     once per attempt with (iteration, state, Z, U, J_opt)."""

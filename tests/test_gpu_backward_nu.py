@@ -105,3 +105,28 @@ print("ok", n)
     env = dict(os.environ, PDDP_FORCE_BACKWARD_NU="1", PYTHONPATH=root)
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_stock_rendezvous_cost_degenerate_quu():
+    """RendezvousCost as shipped (R = 0.1 I) makes Q_uu a multiple of the identity: the reference's
+    (E/e)E^T with LAPACK's non-orthogonal eigenvectors of a repeated eigenvalue is rounding noise, the
+    kernel returns the regularised inverse (oracle with orthonormal eigenvectors).  Whole API path:
+    models.RendezvousDynamicsModel + costs.RendezvousCost -> forward / backward."""
+    import pddp_b200 as P
+    from pddp_b200 import controllers as C
+    torch.manual_seed(3)
+    N, enc = 9, O.IGNORE_UNCERTAINTY
+    model, cost = P.models.RendezvousDynamicsModel(0.1).double(), P.costs.RendezvousCost().double()
+    z0 = torch.tensor([-10.0, -10.0, 10.0, 10.0, 0.0, -5.0, 5.0, 0.0], dtype=torch.float64)
+    U = 0.1 * torch.randn(N, 4, dtype=torch.float64)
+    lin = C.forward(z0.cuda(), U.cuda(), model, cost, enc)
+    ospec = O.QRCostSpec(cost.Q.data, cost.R.data, cost.Q_term.data, cost.x_goal.data, cost.u_goal.data, 8, (),
+                         tuple(range(8)))
+    # (the model's constants are fp32 Parameters widened to fp64, exactly like the reference's)
+    odyn = O.rendezvous_spec(float(model.dt), float(model.m), float(model.alpha))
+    olin = O.linearize(z0, U, odyn, ospec, enc)
+    for got, want in zip(lin, olin):
+        assert rel_err(got.cpu(), want) <= 1e-9
+    k, K = C.backward(*lin, reg=0.5)
+    ok_, oK = O.backward_pass(*olin, reg=0.5, symmetric_eig=True)
+    assert rel_err(k.cpu(), ok_) <= 1e-9 and rel_err(K.cpu(), oK) <= 1e-9

@@ -67,7 +67,8 @@ def test_encoding_matches_oracle(enc):
 
 def test_unsupported_configurations_raise():
     with pytest.raises(NotImplementedError):
-        models.geometry_of(8, ())                      # rendezvous: SURVEY 8f "next"
+        models.geometry_of(5, (1,))                    # no kernels for an arbitrary geometry
+    assert models.geometry_of(8, ()) == _lib.GEO_RENDEZVOUS
     with pytest.raises(NotImplementedError):
         models.bnn_dynamics_model_factory(4, 2, [200, 200], [2], [0, 1, 3])
     Model = models.bnn_dynamics_model_factory(4, 1, [32, 32], [2], [0, 1, 3])

@@ -122,6 +122,10 @@ typedef struct pddp_bnn {
     int32_t input_mode;   /* PDDP_BNN_INPUT_* : how the input particles of step i are formed */
     const void* eps_in;   /* [N, P, D] standardised noise of every step (PDDP_BNN_INPUT_RESAMPLE only;
                              the reference draws eps_in[i] lazily, modules.py:321-329 -- here it is data) */
+    const void* eps_out;  /* [N, P, D] or NULL.  Non-NULL = use_predicted_std=True (modules.py:242-262):
+                             dX_std * exp(log_std head) * eps_out[i] is added to every particle; runs the
+                             CUDA-core MLP kernel (the tcgen05 kernel evaluates the mean head only) */
+    int32_t independent_noise;  /* with eps_out: exp(log_std) is treated as a constant in the derivatives */
 } pddp_bnn;
 
 const char* pddp_version(void);
@@ -188,8 +192,8 @@ int pddp_accept_update(const pddp_shape* shape, const void* J_new, const int32_t
 
 /* ---- BNN dynamics ----------------------------------------------------------------------------
  * pddp_linearize_bnn replaces ilqr.forward with a factory-built BNNDynamicsModel
- * (pddp/models/bnn/modules.py:287-386 + 200-264, eval mode, use_predicted_std=False; the
- * infer_noise_variables / sample_input_distribution options are pddp_bnn.input_mode); pddp_rollout_bnn replaces
+ * (pddp/models/bnn/modules.py:287-386 + 200-264, eval mode; the infer_noise_variables /
+ * sample_input_distribution options are pddp_bnn.input_mode, use_predicted_std is pddp_bnn.eps_out); pddp_rollout_bnn replaces
  * _control_law + _trajectory_cost for the same model.  `workspace` is a device scratch buffer of
  * at least pddp_bnn_workspace_bytes(...) bytes.                                               */
 int64_t pddp_bnn_workspace_bytes(const pddp_shape* shape, const pddp_bnn* bnn, int32_t A);

@@ -111,7 +111,7 @@ ONLY = sys.argv[1:]
 
 
 def run_case(tag, name, enc, dtype, N, seed, bnn=None, bounded=False, reg=1.0, n_alpha=10,
-             fit_iters=0, input_mode="infer"):
+             fit_iters=0, input_mode="infer", pstd=None):
     if ONLY and not any(o in tag for o in ONLY):     # python make_golden.py <substring> ...: subset
         return True
     torch.manual_seed(seed)
@@ -133,6 +133,9 @@ def run_case(tag, name, enc, dtype, N, seed, bnn=None, bounded=False, reg=1.0, n
             model.model.fc_out.bias *= scale_out
         model.eval()
     model_opts = {} if bnn is None else {"use_predicted_std": False, "infer_noise_variables": True}
+    if pstd is not None:                   # "dependent" | "independent" (ref: modules.py:242-262)
+        model_opts["use_predicted_std"] = True
+        model_opts["independent_noise"] = pstd == "independent"
     if input_mode == "resample":
         model_opts["infer_noise_variables"] = False
     elif input_mode == "mean":
@@ -157,6 +160,9 @@ def run_case(tag, name, enc, dtype, N, seed, bnn=None, bounded=False, reg=1.0, n
         odyn.input_mode = input_mode
         if input_mode == "resample":      # the reference drew eps_in[i] for every step during forward()
             odyn.eps_in = torch.stack([model.eps_in[i].data.clone() for i in range(N)]).to(dtype)
+    if pstd is not None:                   # the reference drew eps_out[i] for every step during forward()
+        odyn.eps_out = torch.stack([model.eps_out[i].data.clone() for i in range(N)]).to(dtype)
+        odyn.independent_noise = pstd == "independent"
     olin = O.linearize(z0, U, odyn, ospec_cost, enc, u_min, u_max)
     for n, a, b in zip(NAMES, olin, lin):
         ok &= close(a, b, tol, n)
@@ -203,6 +209,8 @@ def run_case(tag, name, enc, dtype, N, seed, bnn=None, bounded=False, reg=1.0, n
         fx["input_mode"] = {"infer": 0, "resample": 1, "mean": 2}[input_mode]
         if odyn.eps_in is not None:
             fx["eps_in"] = odyn.eps_in
+        if odyn.eps_out is not None:
+            fx["eps_out"], fx["independent_noise"] = odyn.eps_out, int(odyn.independent_noise)
 
     if fit_iters:
         class Env:
@@ -289,6 +297,17 @@ def main():
                    E.FULL_COVARIANCE_MATRIX, f64, 4, 35, bnn=([32, 32], 16, 0.05), input_mode="resample")
     ok &= run_case("bnn_cartpole_ut_resample_f32", "cartpole", E.UPPER_TRIANGULAR_CHOLESKY, f32, 4, 36,
                    bnn=([200, 200], 50, 0.02), input_mode="resample")
+    # use_predicted_std=True: exp(log_std) * eps_out[i] added to every particle
+    ok &= run_case("bnn_cartpole_ut_pstd_small_f64", "cartpole", E.UPPER_TRIANGULAR_CHOLESKY, f64, 5, 51,
+                   bnn=([32, 32], 12, 0.05), pstd="dependent")
+    ok &= run_case("bnn_cartpole_ut_pstd_indep_small_f64", "cartpole", E.UPPER_TRIANGULAR_CHOLESKY, f64, 5, 52,
+                   bnn=([32, 32], 12, 0.05), pstd="independent")
+    ok &= run_case("bnn_double_cartpole_full_pstd_small_f64", "double_cartpole", E.FULL_COVARIANCE_MATRIX, f64,
+                   4, 53, bnn=([32, 32], 16, 0.05), pstd="dependent")
+    ok &= run_case("bnn_cartpole_ut_pstd_f32", "cartpole", E.UPPER_TRIANGULAR_CHOLESKY, f32, 4, 54,
+                   bnn=([200, 200], 50, 0.02), pstd="dependent")
+    ok &= run_case("bnn_cartpole_std_pstd_resample_small_f64", "cartpole", E.STANDARD_DEVIATION_ONLY, f64, 4, 55,
+                   bnn=([32, 32], 12, 0.05), pstd="dependent", input_mode="resample")
     print("ALL OK" if ok else "SOME MISMATCH")
     return 0 if ok else 1
 

@@ -420,6 +420,10 @@ class BNNSpec:
     # (sample_input_distribution=False)
     input_mode: str = "infer"
     eps_in: Optional[torch.Tensor] = None      # [N, P, D], eps_in[0] == eps0 ("resample" only)
+    # use_predicted_std=True (ref: modules.py:242-262): dx += exp(log_std) * eps_out[i], log_std = the second
+    # half of the output layer + log(dX_std); independent_noise detaches exp(log_std)
+    eps_out: Optional[torch.Tensor] = None     # [N, P, D] or None (use_predicted_std=False)
+    independent_noise: bool = False
 
     @property
     def P(self):
@@ -430,11 +434,12 @@ class BNNSpec:
         return BNNSpec([(W.to(dtype), b.to(dtype)) for W, b in self.weights],
                        [m.to(dtype) for m in self.masks], self.eps0.to(dtype), self.D, self.nu,
                        tuple(self.ang), tuple(self.nonang), c(self.X_mean), c(self.X_std_inv),
-                       c(self.dX_mean), c(self.dX_std), self.input_mode, c(self.eps_in))
+                       c(self.dX_mean), c(self.dX_std), self.input_mode, c(self.eps_in), c(self.eps_out),
+                       self.independent_noise)
 
 
-def bnn_particles(spec, X, u):
-    """Particles X:[R,P,D], u:[R,nu] -> next particles [R,P,D] (use_predicted_std=False).
+def bnn_particles(spec, X, u, i=None):
+    """Particles X:[R,P,D], u:[R,nu] -> next particles [R,P,D].
 
     ref: models/bnn/modules.py:200-264; masks are [P,H], shared over the leading dim R.
     """
@@ -446,9 +451,16 @@ def bnn_particles(spec, X, u):
     for (W, b), mask in zip(spec.weights[:-1], spec.masks):
         h = torch.relu((h @ W.mT + b) * mask)
     W, b = spec.weights[-1]
-    dx = (h @ W.mT + b)[..., :spec.D]
+    out = h @ W.mT + b
+    dx, log_std = out[..., :spec.D], out[..., spec.D:]
     if spec.dX_std is not None:
         dx = dx * spec.dX_std + spec.dX_mean
+        log_std = log_std + spec.dX_std.log()
+    if spec.eps_out is not None:                         # use_predicted_std (ref: modules.py:242-262)
+        noise_std = log_std.exp()
+        if spec.independent_noise:
+            noise_std = noise_std.detach()
+        dx = dx + noise_std * spec.eps_out[i]
     return X + dx
 
 
@@ -475,7 +487,7 @@ def bnn_step(spec, z, u, enc, carry=None, i=None):
         delta = (carry - m.unsqueeze(-2)).detach()                       # [R,P,D]
         eps = torch.linalg.solve_triangular(Uc.detach(), delta, upper=True, left=False)
     X = m.unsqueeze(-2) + eps @ Uc
-    Xn = bnn_particles(spec, X, u)
+    Xn = bnn_particles(spec, X, u, i)
     M = Xn.mean(-2)
     if enc in (FULL_COVARIANCE_MATRIX, UPPER_TRIANGULAR_CHOLESKY):
         d = Xn - M.unsqueeze(-2)

@@ -42,7 +42,7 @@ class BNN(C.Structure):
     _fields_ = [("P", C.c_int32), ("H0", C.c_int32), ("H1", C.c_int32)] + [
         (n, C.c_void_p) for n in ("W0", "b0", "W1", "b1", "W2", "b2", "mask0", "mask1", "eps0",
                                   "X_mean", "X_std_inv", "dX_mean", "dX_std")] + [
-        ("input_mode", C.c_int32), ("eps_in", C.c_void_p)]
+        ("input_mode", C.c_int32), ("eps_in", C.c_void_p), ("eps_out", C.c_void_p), ("independent_noise", C.c_int32)]
 
 
 _P = C.c_void_p

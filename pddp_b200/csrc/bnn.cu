@@ -461,7 +461,7 @@ static Workspace<T> carve(void* base, const pddp_shape* s, const pddp_bnn* n, in
     auto take = [&](size_t elems) { T* p = reinterpret_cast<T*>(reinterpret_cast<char*>(base) + off); off += ((elems * sizeof(T) + 255) / 256) * 256; return p; };
     w.W0T = take(K0 * n->H0);
     w.W1T = take((size_t)n->H0 * n->H1);
-    w.W2T = take((size_t)n->H1 * D);
+    w.W2T = take((size_t)n->H1 * 2 * D);
     w.m0T = take((size_t)n->H0 * P);
     w.m1T = take((size_t)n->H1 * P);
     w.Xa = take(S * P * D);
@@ -488,6 +488,8 @@ static BnnNet<T> make_net(const pddp_bnn* n, const Workspace<T>& w) {
     r.mask0T = w.m0T; r.mask1T = w.m1T;
     r.X_mean = (const T*)n->X_mean; r.X_std_inv = (const T*)n->X_std_inv;
     r.dX_mean = (const T*)n->dX_mean; r.dX_std = (const T*)n->dX_std;
+    r.eps_out = (const T*)n->eps_out;                 // step 0; the time loops advance it by P*D per step
+    r.independent_noise = n->independent_noise;
     return r;
 }
 
@@ -507,7 +509,7 @@ static cudaError_t prep_weights(const pddp_shape* s, const pddp_bnn* n, const Wo
     const int DA = s->geo == GEO_PENDULUM ? 3 : s->geo == GEO_CARTPOLE ? 5 : 8;
     bnn_transpose_kernel<T><<<8, 256, 0, st>>>((const T*)n->W0, n->H0, DA + 1, n->H0, w.W0T);
     bnn_transpose_kernel<T><<<64, 256, 0, st>>>((const T*)n->W1, n->H1, n->H0, n->H1, w.W1T);
-    bnn_transpose_kernel<T><<<8, 256, 0, st>>>((const T*)n->W2, 2 * D, n->H1, D, w.W2T);
+    bnn_transpose_kernel<T><<<8, 256, 0, st>>>((const T*)n->W2, 2 * D, n->H1, n->eps_out ? 2 * D : D, w.W2T);
     bnn_transpose_kernel<T><<<16, 256, 0, st>>>((const T*)n->mask0, n->P, n->H0, n->P, w.m0T);
     bnn_transpose_kernel<T><<<16, 256, 0, st>>>((const T*)n->mask1, n->P, n->H1, n->P, w.m1T);
     if (use_tensor_cores<T>(n->H0, n->H1)) {
@@ -529,11 +531,11 @@ static cudaError_t prep_weights(const pddp_shape* s, const pddp_bnn* n, const Wo
 }
 
 // MLP dispatch: SIMT kernel (the tcgen05 kernel hooks in here for fp32 / H = 200)
-template <class T, int GEO, bool TAN, int NJ>
+template <class T, int GEO, bool TAN, int NJ, bool PSTD = false>
 static cudaError_t launch_mlp_simt(const BnnMlpArgs<T>& a, cudaStream_t st) {
     constexpr int RPT = sizeof(T) == 4 ? 8 : 4;
-    typedef MlpSmem<T, GEO, NJ, RPT, TAN> SM;
-    auto kern = bnn_mlp_simt_kernel<T, GEO, NJ, RPT, TAN>;
+    typedef MlpSmem<T, GEO, NJ, RPT, TAN, PSTD> SM;
+    auto kern = bnn_mlp_simt_kernel<T, GEO, NJ, RPT, TAN, PSTD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
     if (e != cudaSuccess) return e;
     const long long ntiles = (a.total + SM::NPART - 1) / SM::NPART;
@@ -558,10 +560,16 @@ static cudaError_t launch_mlp_tc(const BnnMlpArgs<float>& a, const tc::Images& i
 }
 template <class T, int GEO, bool TAN>
 static cudaError_t launch_mlp(const BnnMlpArgs<T>& a, const tc::Images& im, cudaStream_t st) {
+    const int H = a.net.H0 > a.net.H1 ? a.net.H0 : a.net.H1;
+    if (a.net.eps_out) {                     // use_predicted_std: both output heads, CUDA-core kernel
+        if (H <= 32) return launch_mlp_simt<T, GEO, TAN, 2, true>(a, st);
+        if (H <= 208) return launch_mlp_simt<T, GEO, TAN, 13, true>(a, st);
+        if (H <= 256) return launch_mlp_simt<T, GEO, TAN, 16, true>(a, st);
+        return cudaErrorInvalidValue;
+    }
     if (use_tensor_cores<T>(a.net.H0, a.net.H1)) {
         if constexpr (sizeof(T) == 4) return launch_mlp_tc<GEO, TAN>(a, im, st);
     }
-    const int H = a.net.H0 > a.net.H1 ? a.net.H0 : a.net.H1;
     if (H <= 32) return launch_mlp_simt<T, GEO, TAN, 2>(a, st);
     if (H <= 208) return launch_mlp_simt<T, GEO, TAN, 13>(a, st);
     if (H <= 256) return launch_mlp_simt<T, GEO, TAN, 16>(a, st);
@@ -638,6 +646,7 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
             bnn_init_particles_kernel<T, GEO, ENC><<<igrid, 128, 0, c.st>>>(Z, lZ, t, 1, 1, B, P, eps_of(t), c.active, 1,
                                                                             nullptr, cur, c.status);
         a.X = cur; a.Xn = nxt;
+        if (net.eps_out) a.net.eps_out = net.eps_out + (size_t)t * P * D;
         prof_begin(PROF_MLP_LIN, c.st);
         CK((launch_mlp<T, GEO, true>(a, w.im, c.st)));
         prof_end(PROF_MLP_LIN, c.st);
@@ -707,6 +716,7 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     T *cur = w.Xa, *nxt = w.Xb;
     for (int t = 0; t < N; ++t) {
         a.X = cur; a.Xn = nxt;
+        if (net.eps_out) a.net.eps_out = net.eps_out + (size_t)t * P * D;
         prof_begin(PROF_MLP_ROLL, c.st);
         CK((launch_mlp<T, GEO, false>(a, w.im, c.st)));
         prof_end(PROF_MLP_ROLL, c.st);

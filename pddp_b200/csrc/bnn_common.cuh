@@ -12,6 +12,8 @@ struct BnnNet {
     const T *mask0, *mask1, *eps0;             // [P,H0], [P,H1], [P,D]
     const T *mask0T, *mask1T;                  // transposed copies [H0,P], [H1,P] (coalesced when lanes = particles)
     const T *X_mean, *X_std_inv, *dX_mean, *dX_std;   // nullptr = 0 / 1 defaults (ref: modules.py:93-98)
+    const T* eps_out;                                 // [P,D] output noise of the CURRENT step, or nullptr (use_predicted_std=False)
+    int independent_noise;
 };
 
 // Upper Cholesky factor, U^T U = C + jitter*I, reading the upper triangle of C.

@@ -28,20 +28,24 @@ struct BnnMlpArgs {
 constexpr int MLP_KC = 16;
 constexpr int MLP_KP = 16;   // padded layer-0 input width (K0 = DA + nu <= 9)
 
-template <class T, int GEO, int NJ, int RPT, bool TAN>
+// PSTD: use_predicted_std=True -- the log-std head of the output layer (rows D..2D-1 of fc_out) is evaluated
+// too and exp(log_std) * eps_out[i] is added to every particle (ref: modules.py:242-262).
+template <class T, int GEO, int NJ, int RPT, bool TAN, bool PSTD = false>
 struct MlpSmem {
     typedef Geo<GEO> G;
-    static constexpr int D = G::D, K0 = G::DA + G::NU, TD = TAN ? D + G::NU : 0, RPP = 1 + TD;
+    static constexpr int D = G::D, DO = PSTD ? 2 * D : D, K0 = G::DA + G::NU, TD = TAN ? D + G::NU : 0, RPP = 1 + TD;
     static constexpr int RT = 16 * RPT, NPART = RT / RPP, HP = NJ * 16, LDA = HP + 1;
+    static_assert(DO <= MLP_KP, "the output rows reuse the layer-0 input staging");
     static constexpr size_t elems = (size_t)RT * LDA + (size_t)MLP_KC * HP + (TAN ? (size_t)NPART * HP : 0) +
-                                    (size_t)RT * MLP_KP + (size_t)HP * D + (size_t)NPART * D;
+                                    (size_t)RT * MLP_KP + (size_t)HP * DO + (size_t)NPART * D;
     static constexpr size_t bytes = elems * sizeof(T);
 };
 
-template <class T, int GEO, int NJ, int RPT, bool TAN>
+template <class T, int GEO, int NJ, int RPT, bool TAN, bool PSTD = false>
 __global__ void __launch_bounds__(256) bnn_mlp_simt_kernel(const BnnMlpArgs<T> a) {
     typedef Geo<GEO> G;
-    typedef MlpSmem<T, GEO, NJ, RPT, TAN> SM;
+    typedef MlpSmem<T, GEO, NJ, RPT, TAN, PSTD> SM;
+    constexpr int DO = SM::DO;
     constexpr int D = SM::D, K0 = SM::K0, TD = SM::TD, RPP = SM::RPP, RT = SM::RT, NPART = SM::NPART;
     constexpr int HP = SM::HP, LDA = SM::LDA, DA = G::DA, NNA = G::NNA, NANG = G::NANG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -49,14 +53,14 @@ __global__ void __launch_bounds__(256) bnn_mlp_simt_kernel(const BnnMlpArgs<T> a
     T* Wc = A + (size_t)RT * LDA;                   // [KC][HP] chunk of W1T
     T* act = Wc + (size_t)MLP_KC * HP;              // [NPART][HP] primal (pre*mask), TAN only
     T* A0 = act + (TAN ? (size_t)NPART * HP : 0);   // [RT][MLP_KP] layer-0 inputs, later Y[RT][D]
-    T* W2s = A0 + (size_t)RT * MLP_KP;                   // [H1][D]
-    T* xs = W2s + (size_t)HP * D;                   // [NPART][D]
+    T* W2s = A0 + (size_t)RT * MLP_KP;              // [H1][DO]
+    T* xs = W2s + (size_t)HP * DO;                  // [NPART][D]
     const BnnNet<T>& n = a.net;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int H0 = n.H0, H1 = n.H1, P = n.P;
     const long long ntiles = (a.total + NPART - 1) / NPART;
 
-    for (int i = tid; i < H1 * D; i += 256) W2s[i] = n.W2T[i];
+    for (int i = tid; i < H1 * DO; i += 256) W2s[i] = n.W2T[i];     // W2T is [H1][DO] (bnn.cu prep_weights)
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long g0 = tile * NPART;
@@ -194,11 +198,11 @@ __global__ void __launch_bounds__(256) bnn_mlp_simt_kernel(const BnnMlpArgs<T> a
         __syncthreads();
         // ---- phase 3: output layer (H1 -> D), only the mean head is used --------------------
         T* Y = A0;
-        for (int idx = tid; idx < RT * D; idx += 256) {
-            const int row = idx / D, o = idx - row * D;
+        for (int idx = tid; idx < RT * DO; idx += 256) {
+            const int row = idx / DO, o = idx - row * DO;
             T s = T(0);
             const T* ar = A + (size_t)row * LDA;
-            for (int k = 0; k < H1; ++k) s += ar[k] * W2s[k * D + o];
+            for (int k = 0; k < H1; ++k) s += ar[k] * W2s[k * DO + o];
             Y[idx] = s;
         }
         __syncthreads();
@@ -209,11 +213,21 @@ __global__ void __launch_bounds__(256) bnn_mlp_simt_kernel(const BnnMlpArgs<T> a
 #pragma unroll
             for (int o = 0; o < D; ++o) {
                 const T sd = n.dX_std ? n.dX_std[o] : T(1), mn = n.dX_mean ? n.dX_mean[o] : T(0);
-                a.Xn[g * D + o] = xs[tid * D + o] + ((Y[r0 * D + o] + n.b2[o]) * sd + mn);
+                T dx = (Y[r0 * DO + o] + n.b2[o]) * sd + mn;
+                T noise = T(0);                                  // exp(log_std) * eps_out[i][p]   ref: modules.py:254-262
+                if (PSTD) {
+                    noise = sd * jexp(Y[r0 * DO + D + o] + n.b2[D + o]) * n.eps_out[(g % P) * D + o];
+                    dx += noise;
+                    if (n.independent_noise) noise = T(0);       // exp(log_std) detached: no tangent through it
+                }
+                a.Xn[g * D + o] = xs[tid * D + o] + dx;
                 if (TAN) {
 #pragma unroll
-                    for (int d = 0; d < TD; ++d)
-                        a.Jp[(g * D + o) * TD + d] = (d == o ? T(1) : T(0)) + Y[(r0 + 1 + d) * D + o] * sd;
+                    for (int d = 0; d < TD; ++d) {
+                        T j = (d == o ? T(1) : T(0)) + Y[(r0 + 1 + d) * DO + o] * sd;
+                        if (PSTD) j += noise * Y[(r0 + 1 + d) * DO + D + o];
+                        a.Jp[(g * D + o) * TD + d] = j;
+                    }
                 }
             }
         }

@@ -192,12 +192,14 @@ def bnn_dynamics_model_factory(state_size, action_size, hidden_features, angular
                          ("dX_std_inv", 1.0)):
                 self.register_buffer(n, torch.tensor(v))                        # ref: modules.py:93-98
             self.eps_in = {}
+            self.eps_out = {}
 
         def resample(self, generator=None):
             """New eps_in[0] and dropout masks (ref: modules.py:281-285; draw order eps, drop_0, drop_1)."""
             P = self.n_particles
             eps = torch.randn(P, _state_size, generator=generator)
             self.eps_in = {0: (eps - eps.mean(0)) / eps.std(0)}                 # ref: modules.py:321-329
+            self.eps_out = {}
             for name, mod in self.model._modules.items():
                 if isinstance(mod, CDropoutMask):
                     mod.draw(P, self.model._modules["fc_" + name.split("_")[1]].out_features, generator)
@@ -215,6 +217,7 @@ def bnn_dynamics_model_factory(state_size, action_size, hidden_features, angular
                 mask = getattr(drop, "concrete_noise", None)
                 getattr(self.model, "drop_%d" % li).mask = (drop.noise if mask is None else mask).detach().clone()
             self.eps_in = {int(i): e.detach().clone() for i, e in ref_model.eps_in.items()}
+            self.eps_out = {int(i): e.detach().clone() for i, e in getattr(ref_model, "eps_out", {}).items()}
             self.n_particles = self.eps_in[0].shape[0]
             for n in ("X_mean", "X_std", "X_std_inv", "dX_mean", "dX_std", "dX_std_inv"):
                 setattr(self, n, getattr(ref_model, n).detach().clone())
@@ -268,12 +271,22 @@ def bnn_dynamics_model_factory(state_size, action_size, hidden_features, angular
                         eps = torch.randn(self.n_particles, _state_size)
                         self.eps_in[i] = (eps - eps.mean(0)) / eps.std(0)
                 eps_in = torch.stack([self.eps_in[i] for i in range(N)])
+            eps_out = None
+            if opts.get("use_predicted_std", False):        # ref: modules.py:242-262, eps_out[i] drawn on first use
+                if N is None:
+                    raise ValueError("use_predicted_std=True needs the horizon N to lay out eps_out")
+                for i in range(N):
+                    if i not in self.eps_out:
+                        eps = torch.randn(self.n_particles, _state_size)
+                        self.eps_out[i] = (eps - eps.mean(0)) / eps.std(0)
+                eps_out = torch.stack([self.eps_out[i] for i in range(N)])
             m = self.model
             vec = lambda b: None if b.dim() == 0 else b
             return BNNDynamics(geo, [m.fc_0.weight, m.fc_1.weight, m.fc_out.weight],
                                [m.fc_0.bias, m.fc_1.bias, m.fc_out.bias], [m.drop_0.mask, m.drop_1.mask],
                                self.eps_in[0], vec(self.X_mean), vec(self.X_std_inv), vec(self.dX_mean),
-                               vec(self.dX_std), input_mode=mode, eps_in=eps_in)
+                               vec(self.dX_std), input_mode=mode, eps_in=eps_in, eps_out=eps_out,
+                               independent_noise=bool(opts.get("independent_noise", False)))
 
     return BNNDynamicsModel
 
@@ -289,11 +302,12 @@ def _augment(x, ang):
 
 
 def check_model_opts(model, model_opts):
-    """Options the kernels implement: infer_noise_variables and sample_input_distribution either way
-    (BNNDynamics.input_mode); the rest only at the value every reference example uses."""
+    """Options the kernels implement: infer_noise_variables, sample_input_distribution, use_predicted_std and
+    independent_noise either way (BNNDynamics.input_mode / eps_out); resample=True (fresh noise on every call) is
+    not: all noise is data on this path."""
     if not getattr(model, "is_bnn", False):
         return
-    want = dict(use_predicted_std=False, resample=False, independent_noise=False)
+    want = dict(resample=False)
     for k, v in model_opts.items():
         if k in want and bool(v) != want[k]:
             raise NotImplementedError("pddp_b200: model option %s=%r is not built (SURVEY 8f rank 2); supported: %r"

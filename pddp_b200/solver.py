@@ -48,14 +48,17 @@ class BNNDynamics:
     (ref: pddp/models/bnn/modules.py:287-386).  Two hidden layers."""
 
     def __init__(self, geo, weights, biases, masks, eps0, X_mean=None, X_std_inv=None,
-                 dX_mean=None, dX_std=None, input_mode=_lib.BNN_INPUT_INFER, eps_in=None):
+                 dX_mean=None, dX_std=None, input_mode=_lib.BNN_INPUT_INFER, eps_in=None, eps_out=None,
+                 independent_noise=False):
         if len(weights) != 3 or len(biases) != 3 or len(masks) != 2:
             raise NotImplementedError("pddp_b200: the BNN path supports exactly two hidden layers")
         self.geo = geo
         self.is_bnn = True
         self.tensors = dict(W0=weights[0], W1=weights[1], W2=weights[2], b0=biases[0], b1=biases[1],
                             b2=biases[2], mask0=masks[0], mask1=masks[1], eps0=eps0, X_mean=X_mean,
-                            X_std_inv=X_std_inv, dX_mean=dX_mean, dX_std=dX_std, eps_in=eps_in)
+                            X_std_inv=X_std_inv, dX_mean=dX_mean, dX_std=dX_std, eps_in=eps_in, eps_out=eps_out)
+        # eps_out [N,P,D] given = use_predicted_std=True (ref: modules.py:242-262)
+        self.independent_noise = bool(independent_noise)
         # input particles of step i (ref: modules.py:320-358): INFER (default), RESAMPLE = eps_in[i] [N,P,D]
         # at every step (infer_noise_variables=False), MEAN (sample_input_distribution=False)
         self.input_mode = int(input_mode)
@@ -72,6 +75,8 @@ class BNNDynamics:
         if self.input_mode == _lib.BNN_INPUT_RESAMPLE and (
                 eps_in is None or eps_in.dim() != 3 or tuple(eps_in.shape[1:]) != (self.P, D)):
             raise ValueError("BNN_INPUT_RESAMPLE needs eps_in [N,P,D]")
+        if eps_out is not None and (eps_out.dim() != 3 or tuple(eps_out.shape[1:]) != (self.P, D)):
+            raise ValueError("eps_out must be [N,P,D]")
         self._device_copies = {}
 
     def c_struct(self, dtype, device):
@@ -84,6 +89,7 @@ class BNNDynamics:
         s = _lib.BNN()
         s.P, s.H0, s.H1 = self.P, self.H0, self.H1
         s.input_mode = self.input_mode
+        s.independent_noise = int(self.independent_noise)
         for k, v in t.items():
             setattr(s, k, None if v is None else v.data_ptr())
         return s
@@ -174,6 +180,9 @@ class BatchedSolver:
             if dynamics.input_mode == _lib.BNN_INPUT_RESAMPLE and dynamics.tensors["eps_in"].shape[0] < self.N:
                 raise ValueError("BNN_INPUT_RESAMPLE: eps_in holds %d steps, the horizon is %d"
                                  % (dynamics.tensors["eps_in"].shape[0], self.N))
+            if dynamics.tensors["eps_out"] is not None and dynamics.tensors["eps_out"].shape[0] < self.N:
+                raise ValueError("use_predicted_std: eps_out holds %d steps, the horizon is %d"
+                                 % (dynamics.tensors["eps_out"].shape[0], self.N))
             self.c_bnn = dynamics.c_struct(dtype, self.device)
             nbytes = self.lib.pddp_bnn_workspace_bytes(C.byref(self.shape), C.byref(self.c_bnn),
                                                        max_alphas)

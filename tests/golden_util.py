@@ -69,6 +69,8 @@ class Fixture:
         spec = O.BNNSpec(weights, masks, self.t("eps0"), self.D, self.nu, self.ang, self.nonang)
         spec.input_mode = self.input_mode
         spec.eps_in = self.t("eps_in") if self.has("eps_in") else None
+        spec.eps_out = self.t("eps_out") if self.has("eps_out") else None
+        spec.independent_noise = bool(int(self.raw["independent_noise"])) if self.has("independent_noise") else False
         return spec
 
     @property

@@ -25,7 +25,9 @@ def dynamics_from_fixture(fx, device="cuda"):
     return BNNDynamics(GEO[fx.name], [fx.t("W0"), fx.t("W1"), fx.t("W2")],
                        [fx.t("b0"), fx.t("b1"), fx.t("b2")], [fx.t("mask0"), fx.t("mask1")],
                        fx.t("eps0"), input_mode=("infer", "resample", "mean").index(fx.input_mode),
-                       eps_in=fx.t("eps_in") if fx.has("eps_in") else None)
+                       eps_in=fx.t("eps_in") if fx.has("eps_in") else None,
+                       eps_out=fx.t("eps_out") if fx.has("eps_out") else None,
+                       independent_noise=bool(int(fx.raw["independent_noise"])) if fx.has("independent_noise") else False)
 
 
 def solver_from_fixture(fx, B=1, layout=None):

@@ -34,6 +34,10 @@ def build(fx):
             opts["infer_noise_variables"] = False
         elif fx.input_mode == "mean":
             opts["sample_input_distribution"] = False
+        if fx.has("eps_out"):                 # ref: modules.py:242-262
+            model.eps_out = {i: e for i, e in enumerate(fx.t("eps_out"))}
+            opts["use_predicted_std"] = True
+            opts["independent_noise"] = bool(int(fx.raw["independent_noise"]))
     else:
         cls = {"pendulum": models.PendulumDynamicsModel, "cartpole": models.CartpoleDynamicsModel,
                "double_cartpole": models.DoubleCartpoleDynamicsModel,
@@ -46,7 +50,8 @@ def build(fx):
 TAGS = ["known_pendulum_ign_f64", "known_cartpole_ut_bounded_f64", "known_double_cartpole_full_f64",
         "bnn_cartpole_ut_small_f64", "bnn_double_cartpole_full_small_f64", "bnn_cartpole_ut_bounded_f64",
         "bnn_cartpole_ut_resample_small_f64", "bnn_cartpole_ut_mean_small_f64",
-        "known_rendezvous_ign_bounded_f64", "known_rendezvous_ut_f64"]
+        "known_rendezvous_ign_bounded_f64", "known_rendezvous_ut_f64",
+        "bnn_cartpole_ut_pstd_small_f64", "bnn_cartpole_ut_pstd_indep_small_f64"]
 
 
 @pytest.mark.parametrize("tag", TAGS)

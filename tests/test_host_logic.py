@@ -32,7 +32,7 @@ def test_struct_layouts():
     assert ctypes.sizeof(_lib.Shape) == 8 * 4
     assert ctypes.sizeof(_lib.Cost) == (64 + 64 + 16 + 8 + 4) * 8
     assert ctypes.sizeof(_lib.KnownDynamics) == 64
-    assert ctypes.sizeof(_lib.BNN) == 16 + 13 * 8 + 8 + 8     # + input_mode (padded) + eps_in
+    assert ctypes.sizeof(_lib.BNN) == 16 + 13 * 8 + 8 + 8 + 8 + 8     # + input_mode (padded), eps_in, eps_out, independent_noise (padded)
 
 
 def test_no_cpu_fallback():
@@ -74,7 +74,7 @@ def test_unsupported_configurations_raise():
     Model = models.bnn_dynamics_model_factory(4, 1, [32, 32], [2], [0, 1, 3])
     with pytest.raises(NotImplementedError):
         controllers.iLQRController(None, Model(n_particles=8), costs.CartpoleCost(),
-                                   model_opts={"use_predicted_std": True})
+                                   model_opts={"resample": True})
     with pytest.raises(NotImplementedError):
         controllers.backward(*[torch.zeros(1)] * 9, V_zz_reg=True)
 

@@ -218,6 +218,15 @@ int pddp_cost_derivatives(const pddp_shape* shape, const pddp_cost* cost, const 
                           const void* U, const int32_t* active, void* L, void* L_z, void* L_u,
                           void* L_zz, void* L_uz, void* L_uu, void* J_opt, void* stream);
 
+/* ---- ground-truth simulator step (closed-loop MPC / trials) ----------------------------------------
+ * Replaces the step() of the example environments (pddp/examples/<problem>/env.py: x' = model(x, u, 0,
+ * IGNORE_UNCERTAINTY)) behind GymEnv.apply (pddp/envs/gym_env.py:63-73) for B environment instances at
+ * once, so that pddp.controllers.pddp._apply_controller (pddp.py:209-247) never leaves the device.
+ *   in : x[B, D] states, u[B, nu] actions (shape.geo, shape.dtype, shape.B are read; the rest is ignored)
+ *   out: x_next[B, D]  (may alias x)                                                                  */
+int pddp_env_step_known(const pddp_shape* shape, const pddp_known_dynamics* dyn, const void* x, const void* u,
+                        void* x_next, void* stream);
+
 /* ---- instrumentation (bench.py) -----------------------------------------------------------------
  * pddp_profile_enable(1) makes the BNN path bracket its kernels with CUDA events on the launch
  * stream; pddp_profile_read synchronises and returns total milliseconds / launch counts for

@@ -241,6 +241,49 @@ def run_case(tag, name, enc, dtype, N, seed, bnn=None, bounded=False, reg=1.0, n
     return ok
 
 
+def run_closed_loop(tag, name, enc, N, H, seed, bounded, fit_iters=5):
+    """Closed loop on the reference's own environment: controller.fit, then
+    `_apply_controller(env, cost, controller, H, encoding, mpc=True)` (ref: pddp.py:209-247) -- every
+    step is one MPC iteration from the simulator's state -- and an open-loop trial with the fitted U.
+    Everything is built under a float64 default dtype so that the env's own model is fp64 too."""
+    if ONLY and not any(o in tag for o in ONLY):
+        return True
+    from pddp.controllers.pddp import _apply_controller
+    import importlib
+    env_mod = importlib.import_module("pddp.examples.%s.env" % name)
+    env_cls = getattr(env_mod, "".join(w.capitalize() for w in name.split("_")) + "Env")
+    model_cls, cost_cls, _, _, umax = PROBLEMS[name]
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        env = env_cls(dt=DT)
+        model, cost = model_cls(DT), (cost_cls() if name != "rendezvous" else rendezvous_cost_nd()).double()
+        env.reset()
+        x0 = torch.tensor(env._env.state).clone()
+        U0 = 0.1 * torch.randn(N, model_cls.action_size)
+        u_min = torch.full((model_cls.action_size,), -umax) if bounded else None
+        u_max = torch.full((model_cls.action_size,), umax) if bounded else None
+        ctrl = R.iLQRController(env, model, cost)
+        Zf, Uf, st = ctrl.fit(U0.clone(), encoding=enc, n_iterations=fit_iters, quiet=True, u_min=u_min, u_max=u_max)
+        (X, U, dX), J = _apply_controller(env, cost, ctrl, H, enc, True, True, {}, u_min=u_min, u_max=u_max)
+        # open-loop trial of the fitted controls from the same start
+        env._env.state = x0.numpy().copy()
+        env._state = x0.clone()
+        (Xo, Uo, dXo), Jo = _apply_controller(env, cost, Uf, N, enc, False, True, {})
+    finally:
+        torch.set_default_dtype(torch.float32)
+    print("[%s] %s closed loop: fit state %d, mpc J=%.6g, open-loop J=%.6g" % (tag, name, int(st), float(J), float(Jo)))
+    fx = dict(name=name, enc=enc, N=N, H=H, bounded=bounded, fit_iters=fit_iters, x0=x0, U0=U0, fit_Z=Zf, fit_U=Uf,
+              fit_state=int(st), mpc_X=X, mpc_U=U, mpc_dX=dX, mpc_J=J, ol_X=Xo, ol_U=Uo, ol_dX=dXo, ol_J=Jo,
+              Q=cost.Q.data, R=cost.R.data, Q_term=cost.Q_term.data)
+    if bounded:
+        fx.update(u_min=u_min, u_max=u_max)
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"),
+                        **{k_: (v.detach().numpy() if isinstance(v, torch.Tensor) else v) for k_, v in fx.items()})
+    return True
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     f64, f32 = torch.float64, torch.float32
@@ -308,6 +351,10 @@ def main():
                    bnn=([200, 200], 50, 0.02), pstd="dependent")
     ok &= run_case("bnn_cartpole_std_pstd_resample_small_f64", "cartpole", E.STANDARD_DEVIATION_ONLY, f64, 4, 55,
                    bnn=([32, 32], 12, 0.05), pstd="dependent", input_mode="resample")
+    # closed loop on the simulator
+    ok &= run_closed_loop("loop_pendulum_ign_bounded", "pendulum", E.IGNORE_UNCERTAINTY, 15, 8, 61, True)
+    ok &= run_closed_loop("loop_cartpole_ut", "cartpole", E.UPPER_TRIANGULAR_CHOLESKY, 12, 6, 62, False)
+    ok &= run_closed_loop("loop_rendezvous_ign_bounded", "rendezvous", E.IGNORE_UNCERTAINTY, 10, 5, 63, True)
     print("ALL OK" if ok else "SOME MISMATCH")
     return 0 if ok else 1
 

@@ -2,7 +2,7 @@
 linearise -> backward Riccati -> rollout with parallel line search, behind pddp's controller /
 model / cost API.  CUDA kernels live in pddp_b200/csrc and are reached through the C ABI declared
 in include/pddp_b200.h; there is no CPU fallback."""
-from . import controllers, costs, encoding, examples, models  # noqa: F401
+from . import controllers, costs, encoding, envs, examples, models  # noqa: F401
 from .controllers import PDDPController, iLQRController, iLQRState  # noqa: F401
 from .encoding import GaussianVariable, StateEncoding  # noqa: F401
 

@@ -62,6 +62,7 @@ _SIGNATURES = {
                            + [_P, C.c_int64, _P]),
     "pddp_rollout_bnn": (C.c_int, [C.POINTER(Shape), C.POINTER(BNN), C.POINTER(Cost)] + [_P] * 5
                          + [C.c_int32] + [_P] * 10 + [_P, C.c_int64, _P]),
+    "pddp_env_step_known": (C.c_int, [C.POINTER(Shape), C.POINTER(KnownDynamics)] + [_P] * 4),
     "pddp_profile_enable": (None, [C.c_int]),
     "pddp_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pddp_launch_count": (C.c_int64, []),

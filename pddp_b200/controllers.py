@@ -203,7 +203,8 @@ class PDDPController(iLQRController):
                 Ui = U if i == 0 else sampling_noise * torch.rand_like(U)
                 if i > 0 and u_min is not None and u_max is not None:
                     Ui = (u_max - u_min) * Ui + u_min
-                new_data = _apply_controller(self.env, Ui, U.shape[0], encoding, False, u_min=u_min, u_max=u_max)
+                new_data, _ = _apply_controller(self.env, self.cost, Ui, U.shape[0], encoding, False, quiet,
+                                                self._cost_opts, u_min=u_min, u_max=u_max)
                 dataset = _concat_datasets(dataset, new_data, max_dataset_size)
                 if callable(on_trial):
                     on_trial(total_trials, new_data[0], new_data[1])
@@ -219,8 +220,8 @@ class PDDPController(iLQRController):
             Z, U, state = super().fit(U, encoding=encoding, quiet=quiet, u_min=u_min, u_max=u_max, **kwargs)
             if not self.training:
                 break
-            new_data = _apply_controller(self.env, self, 2 * U.shape[0], encoding, True, u_min=u_min, u_max=u_max,
-                                         **kwargs)
+            new_data, _ = _apply_controller(self.env, self.cost, self, 2 * U.shape[0], encoding, True, quiet,
+                                            self._cost_opts, u_min=u_min, u_max=u_max, **kwargs)
             if callable(on_trial):
                 on_trial(total_trials, new_data[0], new_data[1])
             dataset = _concat_datasets(dataset, new_data, max_dataset_size)
@@ -232,22 +233,32 @@ class PDDPController(iLQRController):
         return Z, U, state
 
 
-def _apply_controller(env, controller, H, encoding, mpc=False, **kwargs):
-    """ref: pddp/controllers/pddp.py:209-247 (returns the (X, U, dX) dataset of the trial)."""
+def _apply_controller(env, cost, controller, H, encoding, mpc=False, quiet=False, cost_opts={}, **kwargs):
+    """ref: pddp/controllers/pddp.py:209-247 -> ((X, U, dX), J): runs `controller` (a feedback / MPC
+    controller, or a tensor of open-loop controls) on `env` for H steps and returns the trial's dataset
+    and cost.  With a device environment (pddp_b200.envs) nothing leaves the GPU: the simulator step is
+    `pddp_env_step_known`, every MPC step is one batched iteration of the hot path, and B instances
+    ([B, nz] states, [B, nu] actions) run at once; the dataset is then [B*H, ...] and J is [B]."""
     Z, U = [], []
     open_loop = controller if isinstance(controller, torch.Tensor) else None
+    dev = open_loop.device if open_loop is not None else controller._U_nominal.device
     for i in range(H):
-        z = env.get_state().encode(encoding)
+        z = env.get_state().encode(encoding).to(dev)
         Z.append(z)
-        u = open_loop[i] if open_loop is not None else controller(z.to(controller._U_nominal.device), i, encoding,
-                                                                  mpc, **kwargs)
+        if open_loop is not None:
+            u = open_loop[:, i] if open_loop.dim() == 3 else open_loop[i]
+        else:
+            u = controller(z, i, encoding, mpc, **kwargs)
         U.append(u)
         env.apply(u)
-    Z.append(env.get_state().encode(encoding))
-    Z = torch.stack([z.cpu() for z in Z])
-    U = torch.stack([u.cpu() for u in U])
+    Z.append(env.get_state().encode(encoding).to(dev))
+    Z, U = torch.stack(Z).detach(), torch.stack(U).detach()          # [H+1, (B,) nz], [H, (B,) nu]
+    J = _trajectory_cost(cost, Z, U, encoding, cost_opts) if Z.is_cuda else None
     X = decode_mean(Z, encoding, getattr(env, "state_size", None))
-    return X[:-1].detach(), U.detach(), (X[1:] - X[:-1]).detach()
+    X, dX = X[:-1], X[1:] - X[:-1]
+    if Z.dim() == 3:                                                 # instance-major rows, like B trials back to back
+        X, U, dX = (t.transpose(0, 1).reshape(-1, t.shape[-1]) for t in (X, U, dX))
+    return (X, U, dX), J
 
 
 def _concat_datasets(first, second, max_dataset_size=None):

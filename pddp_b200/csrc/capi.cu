@@ -120,6 +120,28 @@ extern "C" int pddp_linearize_known(const pddp_shape* s, const pddp_known_dynami
 
 // ---------------------------------------------------------------------------------------------
 template <class T>
+static int env_step_t(const pddp_shape* s, const pddp_known_dynamics* dyn, const void* x, const void* u, void* xn,
+                      cudaStream_t st) {
+    KnownParams<T> kp;
+    for (int i = 0; i < 8; ++i) kp.p[i] = (T)dyn->p[i];
+    note_launches(1);
+    if (s->geo == GEO_RENDEZVOUS) return cuda_result(env_step_lq<T>(s->B, kp, (const T*)x, (const T*)u, (T*)xn, st), "pddp_env_step_known");
+    return cuda_result(env_step_known<T>(s->geo, s->B, kp, (const T*)x, (const T*)u, (T*)xn, st), "pddp_env_step_known");
+}
+
+extern "C" int pddp_env_step_known(const pddp_shape* s, const pddp_known_dynamics* dyn, const void* x, const void* u,
+                                   void* x_next, void* stream) {
+    if (!s) return fail(PDDP_E_BADARG, "shape is NULL");
+    if (geo_D(s->geo) < 0) return fail(PDDP_E_UNSUPPORTED, "unsupported geometry");
+    if (s->dtype != PDDP_F32 && s->dtype != PDDP_F64) return fail(PDDP_E_BADARG, "dtype must be PDDP_F32 or PDDP_F64");
+    if (s->B < 1 || !dyn || !x || !u || !x_next) return fail(PDDP_E_BADARG, "pddp_env_step_known: NULL argument / B < 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->dtype == PDDP_F32) return env_step_t<float>(s, dyn, x, u, x_next, st);
+    return env_step_t<double>(s, dyn, x, u, x_next, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class T>
 static int backward_t(const pddp_shape* s, const void* F_z, const void* F_u, const void* L_z, const void* L_u,
                       const void* L_zz, const void* L_uz, const void* L_uu, const double* mu, const void* U,
                       const void* u_min, const void* u_max, const int32_t* active, void* k, void* K,

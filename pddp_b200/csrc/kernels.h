@@ -57,6 +57,8 @@ struct CostDerivArgs {
 
 template <class T> cudaError_t linearize_known(int geo, int enc, const LinKnownArgs<T>&, cudaStream_t);
 template <class T> cudaError_t rollout_known(int geo, int enc, const RollKnownArgs<T>&, cudaStream_t);
+template <class T> cudaError_t env_step_known(int geo, int B, const KnownParams<T>&, const T* x, const T* u, T* xn, cudaStream_t);
+template <class T> cudaError_t env_step_lq(int B, const KnownParams<T>&, const T* x, const T* u, T* xn, cudaStream_t);
 template <class T> cudaError_t linearize_lq(int enc, const LinKnownArgs<T>&, cudaStream_t);      // known_lq.cu (rendezvous)
 template <class T> cudaError_t rollout_lq(int enc, const RollKnownArgs<T>&, cudaStream_t);
 template <class T> cudaError_t cost_derivatives_lq(int enc, const CostDerivArgs<T>&, cudaStream_t);

@@ -292,6 +292,36 @@ static cudaError_t launch_roll(const RollKnownArgs<T>& a, cudaStream_t s) {
         default: return cudaErrorInvalidValue;                                                    \
     }
 
+// ------------------------------------------------------------------------------------------
+// ground-truth simulator step of the example environments, thread = environment instance
+// (ref: examples/*/env.py step(): x' = model(x, u, 0, IGNORE_UNCERTAINTY))
+// ------------------------------------------------------------------------------------------
+template <class T, int GEO>
+__global__ void __launch_bounds__(128) env_step_kernel(int B, KnownParams<T> dyn, const T* x, const T* u, T* xn) {
+    constexpr int D = Geo<GEO>::D;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    T xi[D], xo[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) xi[i] = x[(int64_t)b * D + i];
+    known_mean_step<GEO, T, T>(dyn, xi, u[b], xo);
+#pragma unroll
+    for (int i = 0; i < D; ++i) xn[(int64_t)b * D + i] = xo[i];
+}
+template <class T>
+cudaError_t env_step_known(int geo, int B, const KnownParams<T>& dyn, const T* x, const T* u, T* xn, cudaStream_t s) {
+    const int th = 128, grid = (B + th - 1) / th;
+    switch (geo) {
+        case GEO_PENDULUM: env_step_kernel<T, GEO_PENDULUM><<<grid, th, 0, s>>>(B, dyn, x, u, xn); break;
+        case GEO_CARTPOLE: env_step_kernel<T, GEO_CARTPOLE><<<grid, th, 0, s>>>(B, dyn, x, u, xn); break;
+        case GEO_DOUBLE_CARTPOLE: env_step_kernel<T, GEO_DOUBLE_CARTPOLE><<<grid, th, 0, s>>>(B, dyn, x, u, xn); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+template cudaError_t env_step_known<PDDP_KNOWN_T>(int, int, const KnownParams<PDDP_KNOWN_T>&, const PDDP_KNOWN_T*,
+                                                  const PDDP_KNOWN_T*, PDDP_KNOWN_T*, cudaStream_t);
+
 template <class T>
 cudaError_t linearize_known(int geo, int enc, const LinKnownArgs<T>& a, cudaStream_t s) {
     PDDP_DISPATCH_GEO_ENC(launch_lin, geo, enc, a, s)

@@ -376,6 +376,28 @@ cudaError_t linearize_lq(int enc, const LinKnownArgs<T>& a, cudaStream_t s) {
 }
 
 template <class T>
+__global__ void __launch_bounds__(128) lq_env_step_kernel(int B, KnownParams<T> dyn, const T* x, const T* u, T* xn) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const RdvModel<T> md = rdv_model(dyn);
+    T xi[RD], ui[RNU], xo[RD];
+#pragma unroll
+    for (int i = 0; i < RD; ++i) xi[i] = x[(int64_t)b * RD + i];
+#pragma unroll
+    for (int i = 0; i < RNU; ++i) ui[i] = u[(int64_t)b * RNU + i];
+    rdv_mean_step(md, xi, ui, xo);
+#pragma unroll
+    for (int i = 0; i < RD; ++i) xn[(int64_t)b * RD + i] = xo[i];
+}
+template <class T>
+cudaError_t env_step_lq(int B, const KnownParams<T>& dyn, const T* x, const T* u, T* xn, cudaStream_t s) {
+    lq_env_step_kernel<T><<<(B + 127) / 128, 128, 0, s>>>(B, dyn, x, u, xn);
+    return cudaGetLastError();
+}
+template cudaError_t env_step_lq<float>(int, const KnownParams<float>&, const float*, const float*, float*, cudaStream_t);
+template cudaError_t env_step_lq<double>(int, const KnownParams<double>&, const double*, const double*, double*, cudaStream_t);
+
+template <class T>
 cudaError_t cost_derivatives_lq(int enc, const CostDerivArgs<T>& a, cudaStream_t s) {
     const int th = 64;
     const unsigned grid = (unsigned)(((int64_t)a.B * (a.N + 1) + th - 1) / th);

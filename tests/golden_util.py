@@ -21,7 +21,18 @@ SPEC_FN = {"pendulum": O.pendulum_spec, "cartpole": O.cartpole_spec,
 
 
 def all_tags():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Per-pass fixtures (known_* / bnn_*); the closed-loop fixtures (loop_*) have their own loader."""
+    return sorted(t for t in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+                  if not t.startswith("loop_"))
+
+
+def loop_tags():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "loop_*.npz")))
+
+
+def load_raw(tag):
+    raw = np.load(os.path.join(GOLDEN_DIR, tag + ".npz"), allow_pickle=False)
+    return {k: (torch.from_numpy(np.array(raw[k])) if raw[k].ndim else raw[k].item()) for k in raw.files}
 
 
 class Fixture:

@@ -133,3 +133,50 @@ def test_bnn_model_draws_reference_style_state():
     for mask in (m.model.drop_0.mask, m.model.drop_1.mask):
         assert mask.shape == (50, 200) and 0 <= float(mask.min()) and float(mask.max()) <= 1
     assert tuple(m.model.fc_0.weight.shape) == (200, 6) and tuple(m.model.fc_out.weight.shape) == (8, 200)
+
+
+def test_bnn_model_options_map_to_the_descriptor():
+    """infer_noise_variables / sample_input_distribution / use_predicted_std / independent_noise
+    (ref: pddp/models/bnn/modules.py:242-262, 320-358) -> BNNDynamics.input_mode / eps_in / eps_out;
+    noise the reference would draw lazily is drawn per step, standardised, and then kept."""
+    Model = models.bnn_dynamics_model_factory(4, 1, [32, 32], [2], [0, 1, 3])
+    m = Model(n_particles=9)
+    m.resample(torch.Generator().manual_seed(0))
+    d = m.descriptor({}, 6)
+    assert d.input_mode == _lib.BNN_INPUT_INFER and d.tensors["eps_in"] is None and d.tensors["eps_out"] is None
+    d = m.descriptor({"sample_input_distribution": False}, 6)
+    assert d.input_mode == _lib.BNN_INPUT_MEAN
+    d = m.descriptor({"infer_noise_variables": False, "use_predicted_std": True, "independent_noise": True}, 6)
+    assert d.input_mode == _lib.BNN_INPUT_RESAMPLE and d.independent_noise
+    assert tuple(d.tensors["eps_in"].shape) == (6, 9, 4) and tuple(d.tensors["eps_out"].shape) == (6, 9, 4)
+    assert torch.equal(d.tensors["eps_in"][0], m.eps_in[0])
+    for e in (d.tensors["eps_in"][3], d.tensors["eps_out"][5]):
+        assert torch.allclose(e.mean(0), torch.zeros(4), atol=1e-6) and torch.allclose(e.std(0), torch.ones(4), atol=1e-6)
+    again = m.descriptor({"infer_noise_variables": False, "use_predicted_std": True}, 4)
+    assert torch.equal(again.tensors["eps_in"], d.tensors["eps_in"][:4])        # drawn once, then persistent
+    assert torch.equal(again.tensors["eps_out"], d.tensors["eps_out"][:4])
+    with pytest.raises(ValueError):
+        m.descriptor({"infer_noise_variables": False})                          # horizon needed to lay eps_in out
+    with pytest.raises(ValueError):
+        from pddp_b200.solver import BNNDynamics
+        t = d.tensors
+        BNNDynamics(d.geo, [t["W0"], t["W1"], t["W2"]], [t["b0"], t["b1"], t["b2"]], [t["mask0"], t["mask1"]],
+                    t["eps0"], input_mode=_lib.BNN_INPUT_RESAMPLE)              # RESAMPLE without eps_in
+
+
+def test_rendezvous_and_envs_host_side():
+    """action_size 4 constants reach the C structs; environments refuse to live on the CPU."""
+    from pddp_b200 import envs
+    c = costs.RendezvousCost()
+    assert c.Q[0, 2] == -1 and c.Q[3, 1] == -1 and c.R.shape == (4, 4) and c.Q_term.equal(c.Q)
+    s = c.constants().c_struct()
+    assert [s.R[i] for i in (0, 1, 5, 15)] == pytest.approx([0.1, 0.0, 0.1, 0.1])
+    assert list(s.u_goal) == [0.0] * 4
+    m = models.RendezvousDynamicsModel(0.1)
+    assert (m.state_size, m.action_size) == (8, 4) and m.descriptor().geo == _lib.GEO_RENDEZVOUS
+    assert m.descriptor().params == pytest.approx([0.1, 1.0, 0.1])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        envs.PendulumEnv(dt=0.1, device="cpu")
+    names = list(inspect.signature(controllers._apply_controller).parameters)
+    assert names[:8] == ["env", "cost", "controller", "H", "encoding", "mpc", "quiet", "cost_opts"]   # ref: pddp.py:209-217
+    assert pddp_b200.examples.rendezvous.RendezvousEnv is envs.RendezvousEnv

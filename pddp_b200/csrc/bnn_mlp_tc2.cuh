@@ -1,355 +1,130 @@
-// Particle MLP on the 5th-generation tensor cores (tcgen05 + TMEM), fp32 in / fp32 out.
+// Particle MLP on the tensor cores, CTA-PAIR version of bnn_mlp_tc.cuh (tcgen05 cta_group::2).
 //
-//   X'_p = X_p + dX_std * fc_out(relu(M1_p * fc_1(relu(M0_p * fc_0(norm([aug(X_p), u])))))) + dX_mean
-//   (ref: pddp/models/bnn/modules.py:200-264, 774-789; dropout masks are [P,H], one row per particle)
-// and, for the linearisation, its Jacobian w.r.t. (X_p, u) by forward-mode tangents that share the
-// primal's activation pattern.
-//
-// Design (measurements and the road here: profiles/r1_summary.md):
-//   * a tile holds 128 items of ONE particle p (rows gathered with stride P), so the dropout masks
-//     are per-column constants of the tile: M0_p is folded into a per-particle image of W0|b0
-//     (relu(m*x) = m*relu(x), m >= 0) and M1_p into a per-particle copy of the output weights --
-//     no mask is read in the inner loops;
-//   * layer 0 runs on the tensor core too: A0 = [norm(aug(X),u), 1] (K padded to 8/16) times the
-//     per-particle image, split FP16 like layer 1, 32 hidden units at a time into a small TMEM accumulator.  Row
-//     H0 of the image is the unit vector of the bias column, so hidden unit H0 is the constant 1
-//     that carries b1 through the second GEMM (b1 is column H0 of the W1 image);
-//   * layer 1 (the 200x200 contraction) runs in split FP16, a0*b0 + a0*b1 + a1*b0 with fp32
-//     accumulation: fp32-class accuracy from three FP16 passes and 4 operand bytes per element;
-//   * tangents are pass-major: a super-tile is the primal pass followed by one pass per direction
-//     over the same 128 items, so a thread meets the primal and the tangent pre-activation of the
-//     same (item, hidden unit) and the ReLU gate is a register bit mask, never a shuffle;
-//   * two independent tile "tracks" per CTA consume the same streamed W1 K-block (16 wide,
-//     SWIZZLE_64B rows of [b0 | b1]): half the L2->smem traffic per row.  Track 1 runs half a tile behind track 0,
-//     and each track has its own layer-1 issuer thread, so one track's epilogue is covered by the
-//     other's MMAs (they can drift NB W1 stages apart);
-//   * warp roles (20 warps): per track 4 epilogue warps (16x256b TMEM fragments, output layer on
-//     the CUDA cores with quad-shuffle column sums), 4 mid-stage warps (tcgen05.ld of the layer-0
-//     chunk, ReLU / gate, hi-lo split, st.shared into the UMMA K-major layout) and one layer-1
-//     MMA-issuer thread; one polling layer-0 issuer thread for both tracks; one bulk-copy loader.
-//
-// TMEM (512 columns): track t owns columns [256t, 256t+208) for the layer-1 accumulator and
-// [256t+208, 256t+240) for the layer-0 chunk.
+// Same roles, tiles, images and arithmetic as bnn_mlp_tc_kernel; what changes is who feeds the MMAs.  The
+// single-CTA kernel is bound by the shared-memory data pipe (profiles/r1_summary.md: 98 % busy with MMA operand
+// fetch + LDS/STS + bulk-copy fill).  Here two CTAs of a cluster (one TPC) work on one 256-row tile per track:
+// every MMA is M = 256 and is issued by the leader CTA; each CTA supplies its own 128 rows of A and only
+// HALF of B (104 of the 208 W1 rows, 16 of the 32 layer-0 rows) -- the tensor cores exchange the B halves --
+// so per CTA the B operand fetch and the bulk-copy fill are halved (~20 % fewer shared-memory wavefronts per tile).
+//   * consumer -> issuer barriers (a0_full, acc0_empty, a1_full, acc1_empty) live in the leader and count the
+//     producer threads of BOTH CTAs (the peer arrives remotely, mapa + mbarrier.arrive.release.cluster);
+//   * issuer -> consumer signals are tcgen05.commit.cta_group::2 ... multicast::cluster to the barrier at the
+//     same offset in both CTAs (acc0_full, a1_empty, b_empty, acc1_full);
+//   * each CTA bulk-copies its half of every W1 K-block / layer-0 image; the peer's otherwise idle issuer warps
+//     relay "landed" to the leader (b_peer, w0_peer).
 #pragma once
-#include "bnn_mlp_simt.cuh"
-#include <cuda_fp16.h>
-#include <type_traits>
+#include "bnn_mlp_tc.cuh"
 
 namespace pddp {
 namespace tc {
 
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+constexpr int B_HALF = B_STAGE / 2;       // 104 rows x 64 B
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
-// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the
-// hint expires.  Without a hint the default window is ~50 cycles: the waiting roles re-polled 60 M
-// times per launch, and the kernel runs into the board's power cap.
-constexpr uint32_t MBAR_SUSPEND_NS = 20000;
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void arrive_leader(uint64_t* bar, uint32_t rank) {
+    if (rank == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    else mbar_arrive_remote(bar, 0);
+}
+// one arrival per warp: a remote mbarrier.arrive is a DSMEM transaction (~200 cycles, low throughput); 128 of them per
+// barrier phase made the pair kernel 2x SLOWER than the single-CTA one
+__device__ __forceinline__ void warp_arrive_leader(uint64_t* bar, uint32_t rank, int lane) {
+    __syncwarp();
+    if (lane == 0) arrive_leader(bar, rank);
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra.uni WAIT_DONE;\n\t"
-        "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_NS) : "memory");
+        "WAIT_LOOP_C:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra.uni WAIT_DONE_C;\n\t"
+        "bra.uni WAIT_LOOP_C;\n\t"
+        "WAIT_DONE_C:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_NS) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-constexpr int TILE_M = 128, TILE_N = 208, KB = 16, MAX_NKB = 13, MAX_NCH = 7, N0 = 32;
-// Layer 1 in split FP16: a = a0 + a1, b = b0 + b1 with a0 = fp16(a), a1 = fp16(a - a0) (22
-// significand bits together) and a*b ~ a0*b0 + a0*b1 + a1*b0 accumulated in fp32 by the tensor
-// core -- three FP16 passes of K = 16 per K-block.  That is fp32-class accuracy (the dropped a1*b1
-// is 2^-24 of the product) for 3/4 of the tensor time and 5/8..1/2 of the shared-memory and L2
-// bytes of TF32-based splitting (a 4-byte [a0 | a1] pair per element instead of 8 bytes), which
-// matters because the kernel is bound by the shared-memory data pipe (profiles/r1_summary.md).
-// FP16 range: the W1 image is scaled by a power of two so that max |w| * scale is ~2^14 (the lo
-// parts stay normal); the scale is undone inside the per-particle output weights.  Hidden
-// activations must stay below 65504 (they are O(1) for any network that rolls out finitely).
-constexpr int B_STAGE = TILE_N * 64;   // W1 K-block: 208 rows x [b0 (16 fp16) | b1 (16 fp16)], 13 312 B
-constexpr int A1_SLOT = TILE_M * 64;   // 128 rows x [a0 (16 fp16) | a1 (16 fp16)], 8 192 B
-constexpr int THREADS = 20 * 32;
-constexpr int TM_ACC1 = 0, TM_ACC0 = 208, TM_TRACK = 256;
-
-// byte offset of element (row, kk) in a K-major tile whose rows are ROWB bytes (32 / 64 / 128 =
-// SWIZZLE_32B / 64B / 128B): 16-byte chunk index XORed with the matching bits of the row index.
-template <int ROWB>
-__host__ __device__ __forceinline__ uint32_t swz(int row, int kk) {
-    constexpr int SH = ROWB == 32 ? 2 : ROWB == 64 ? 1 : 0;
-    const int chunk = (kk >> 2) ^ ((row & 7) >> SH);
-    return (uint32_t)((row >> 3) * (8 * ROWB) + (row & 7) * ROWB + (chunk << 4) + (kk & 3) * 4);
-}
-// same, for a byte position inside the row
-template <int ROWB>
-__host__ __device__ __forceinline__ uint32_t swz_byte(int row, int byte) {
-    constexpr int SH = ROWB == 32 ? 2 : ROWB == 64 ? 1 : 0;
-    return (uint32_t)((row >> 3) * (8 * ROWB) + (row & 7) * ROWB + ((((byte >> 4) ^ ((row & 7) >> SH))) << 4) + (byte & 15));
-}
-// K-major shared-memory descriptor for rows of ROWB bytes (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) addr>>4, [16,30) LBO>>4 = 1, [32,46) SBO>>4 = 8 rows, [46,48) version 1, [61,64) layout type.
-template <int ROWB>
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    constexpr uint64_t LT = ROWB == 32 ? 6 : ROWB == 64 ? 4 : 2;
-    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((8 * ROWB) >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= LT << 61;
-    return d;
-}
-
-
-// two floats -> packed fp16x2 (a in the low half = lower address)
-__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
-    uint32_t d;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
-    return d;
-}
-__device__ __forceinline__ float2 unpack_f16(uint32_t h) {
-    return __half22float2(*reinterpret_cast<const __half2*>(&h));
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ void sts128f(uint32_t addr, float x, float y, float z, float w) {
-    sts128(addr, __float_as_uint(x), __float_as_uint(y), __float_as_uint(z), __float_as_uint(w));
-}
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-// packed fp32 pairs for FFMA2 (fma.rn.f32x2: two fp32 FMAs per issue slot; nvcc does not generate it on its own)
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float lo2(unsigned long long v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-__device__ __forceinline__ float hi2(unsigned long long v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
-        "r"(accumulate) : "memory");
-}
-constexpr uint32_t idesc_f16(int M, int N) {      // A, B = F16 (format 0), D = F32
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-// 16 lanes x 256 bit fragments: register 4i+{0,1} = row lane/4, columns 8i + 2*(lane%4) + {0,1};
-// register 4i+{2,3} = row lane/4 + 8, same columns (measured with tools/probe/tmem_layout.cu).
-__device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld8(float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
-                 :: "memory");
-}
-// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled
-// above the wait.
-__device__ __forceinline__ void tc_wait_ld16(float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :: "memory");
-}
-__device__ __forceinline__ void tc_wait_ld32(float* v) {
-    tc_wait_ld16(v);
-    tc_wait_ld16(v + 16);
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_test_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// true in exactly one lane of a converged warp
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+__device__ __forceinline__ void tc_mma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate) : "memory");
+}
+
+// waits without a suspend-time hint (experiment: are remotely completed phases slow to wake a suspended waiter?)
+__device__ __forceinline__ void mbar_wait_fast(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP_F:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE_F;\n\t"
+        "bra.uni WAIT_LOOP_F;\n\t"
+        "WAIT_DONE_F:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_fast(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP_G:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE_G;\n\t"
+        "bra.uni WAIT_LOOP_G;\n\t"
+        "WAIT_DONE_G:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 template <int K0P, int DP>
-struct Cfg {
-    static constexpr int NB = K0P == 8 ? 5 : 4;    // W1 K-block stages
-    static constexpr int NS = K0P == 8 ? 6 : 4;    // layer-1 A-operand slots per track
-    static constexpr int ROWB0 = K0P * 4;          // layer-0 operand row [x0 (K0P fp16) | x1 (K0P fp16)]: SWIZZLE_32B / 64B
+struct Cfg2 {
+    static constexpr int NB = K0P == 8 ? 7 : 6;    // W1 K-block stages (half blocks: 6.5 KB each)
+    static constexpr int NS = K0P == 8 ? 8 : 6;    // layer-1 A-operand slots per track (deeper than the single-CTA kernel:
+                                                   // the shared memory freed by the half blocks covers the cross-CTA hops)
+    static constexpr int ROWB0 = K0P * 4;
     static constexpr int A0_BYTES = TILE_M * ROWB0;
     static constexpr int W0_CHUNK_PART = N0 * ROWB0, W0_CHUNK = 2 * W0_CHUNK_PART, W0_BYTES = MAX_NCH * W0_CHUNK;
+    static constexpr int W0_PAD = 1024;            // >= 16 rows of the layer-0 image (the peer's early landing)
     static constexpr int W2_BYTES = TILE_N * DP * 4;
     static constexpr int B_OFF = 0;
-    static constexpr int A1_OFF = B_OFF + NB * B_STAGE;
+    static constexpr int A1_OFF = B_OFF + NB * B_HALF;
     static constexpr int A0_OFF = A1_OFF + 2 * NS * A1_SLOT;
-    static constexpr int W0_OFF = A0_OFF + 2 * A0_BYTES;
+    static constexpr int W0_OFF = A0_OFF + 2 * A0_BYTES + W0_PAD;
     static constexpr int W2_OFF = W0_OFF + 2 * W0_BYTES;
     static constexpr int BAR_OFF = W2_OFF + 2 * W2_BYTES;
-    static constexpr int NBARS = 2 * NB + 4 * NS + 14;
+    static constexpr int NBARS = 2 * NB + 4 * NS + 14 + NB + 2;
     static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
     static constexpr int ALIGN_PAD = 512;
-};
-
-// ---- one-time images (global memory, L2 resident) -------------------------------------------
-// scale[0] = power of two with max(|W1|, |b1|) * scale in [2^13, 2^14]; scale[1] = 1 / scale[0]
-__global__ void prep_scale_kernel(const float* W1, const float* b1, int H0, int H1, float* scale) {
-    __shared__ float red[256];
-    float m = 0.f;
-    for (int i = threadIdx.x; i < H0 * H1; i += blockDim.x) m = fmaxf(m, fabsf(W1[i]));
-    for (int i = threadIdx.x; i < H1; i += blockDim.x) m = fmaxf(m, fabsf(b1[i]));
-    red[threadIdx.x] = m;
-    __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        int e = 0;
-        const float mx = red[0];
-        if (mx > 0.f && isfinite(mx)) { frexpf(mx, &e); e = 14 - e; }      // mx = f * 2^(e0), f in [0.5, 1)
-        e = e > 24 ? 24 : (e < -24 ? -24 : e);
-        scale[0] = ldexpf(1.f, e);
-        scale[1] = ldexpf(1.f, -e);
-    }
-}
-// W1 image: [nkb][208 rows x (b0[16] | b1[16]) fp16] SWIZZLE_64B, scaled; column H0 carries the bias b1.
-__global__ void prep_w1_kernel(const float* W1 /*[H1][H0]*/, const float* b1, int H0, int H1, int nkb,
-                               const float* scale, unsigned char* img) {
-    const int total = nkb * TILE_N * KB;
-    const float sc = scale[0];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int kb = i / (TILE_N * KB), rem = i - kb * TILE_N * KB;
-        const int n = rem / KB, kk = rem - n * KB, k = kb * KB + kk;
-        float w = 0.f;
-        if (n < H1) w = k < H0 ? W1[(size_t)n * H0 + k] : (k == H0 ? b1[n] : 0.f);
-        w *= sc;
-        const __half h0 = __float2half_rn(w);
-        const __half h1 = __float2half_rn(w - __half2float(h0));
-        // element kk of [b0 | b1] sits at 2-byte index kk (b0) or 16 + kk (b1) of the 64-byte row
-        unsigned char* row = img + (size_t)kb * B_STAGE + (n >> 3) * 512 + (n & 7) * 64;
-        const int sw = (n >> 1) & 3;
-        *reinterpret_cast<__half*>(row + (((kk >> 3) ^ sw) << 4) + (kk & 7) * 2) = h0;
-        *reinterpret_cast<__half*>(row + (((2 + (kk >> 3)) ^ sw) << 4) + (kk & 7) * 2) = h1;
-    }
-}
-// Per-particle layer-0 image: [P][chunk][X | Y][32 rows], split FP16 like layer 1: with w = b0 + b1 the row
-// of part X is [b0 | b0] and of part Y is [b1 | 0], so that against the operand row [a0 | a1]
-// X gives a0*b0 + a1*b0 and Y gives a0*b1.  Row n < H0 is m0[p][n]*[W0[n][:], b0[n]], row H0 is the unit
-// vector of the bias column (the constant-1 hidden unit), the rest zero.
-template <int K0P>
-__global__ void prep_w0_kernel(const float* W0 /*[H0][K0]*/, const float* b0, const float* mask0 /*[P][H0]*/, int P,
-                               int H0, int K0, unsigned char* img) {
-    typedef Cfg<K0P, 4> C;
-    const int total = P * MAX_NCH * N0 * K0P;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int p = i / (MAX_NCH * N0 * K0P), rem = i - p * (MAX_NCH * N0 * K0P);
-        const int j = rem / (N0 * K0P), rem2 = rem - j * (N0 * K0P);
-        const int rr = rem2 / K0P, k = rem2 - rr * K0P, n = j * N0 + rr;
-        float w = 0.f;
-        if (n < H0) w = mask0[(size_t)p * H0 + n] * (k < K0 ? W0[(size_t)n * K0 + k] : (k == K0 ? b0[n] : 0.f));
-        else if (n == H0) w = k == K0 ? 1.f : 0.f;
-        const __half h0 = __float2half_rn(w);
-        const __half h1 = __float2half_rn(w - __half2float(h0));
-        unsigned char* base = img + (size_t)p * C::W0_BYTES + (size_t)j * C::W0_CHUNK;
-        *reinterpret_cast<__half*>(base + swz_byte<C::ROWB0>(rr, 2 * k)) = h0;
-        *reinterpret_cast<__half*>(base + swz_byte<C::ROWB0>(rr, 2 * (K0P + k))) = h0;
-        *reinterpret_cast<__half*>(base + C::W0_CHUNK_PART + swz_byte<C::ROWB0>(rr, 2 * k)) = h1;
-        *reinterpret_cast<__half*>(base + C::W0_CHUNK_PART + swz_byte<C::ROWB0>(rr, 2 * (K0P + k))) = __float2half_rn(0.f);
-    }
-}
-// Per-particle output weights m1[p][c] * W2[o][c] / scale (mean head only, o < D), stored per COLUMN PAIR as
-// W2p[p][c / 2][o][c % 2] when D <= 4 (the epilogue's FFMA2 takes (column 2j, column 2j+1) of one output as a 64-bit
-// operand), as W2p[p][c][o] otherwise
-__global__ void prep_w2_kernel(const float* W2 /*[2D][H1]*/, const float* mask1 /*[P][H1]*/, int P, int H1, int D, int DP,
-                               const float* scale, float* out) {
-    const bool pairs = D <= 4;
-    const int total = P * TILE_N * DP;
-    const float inv = scale[1];              // the layer-1 accumulator carries the W1 image's scale
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int p = i / (TILE_N * DP), rem = i - p * (TILE_N * DP);
-        const int jp = rem / (2 * DP), rem2 = rem - jp * (2 * DP);
-        const int o = pairs ? rem2 >> 1 : rem % DP, c = pairs ? 2 * jp + (rem2 & 1) : rem / DP;
-        out[i] = (c < H1 && o < D) ? mask1[(size_t)p * H1 + c] * W2[(size_t)o * H1 + c] * inv : 0.f;
-    }
-}
-
-struct Images {
-    const unsigned char* W1img;
-    const unsigned char* W0img;
-    const float* W2p;
-    const float* scale;        // [2]: power-of-two scale of the W1 image and its inverse
+    static_assert(16 * ROWB0 <= W0_PAD && A1_OFF % 512 == 0 && W0_OFF % 512 == 0, "layout");
 };
 
 template <int GEO, bool TAN>
-__global__ void __launch_bounds__(THREADS, 1)
-bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p, int nkb) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p, int nkb) {
     typedef Geo<GEO> G;
     constexpr int D = G::D, DA = G::DA, NNA = G::NNA, NANG = G::NANG, K0 = DA + G::NU;
     constexpr int K0P = K0 + 1 <= 8 ? 8 : 16, DP = D <= 4 ? 4 : 8;
-    typedef Cfg<K0P, DP> C;
+    typedef Cfg2<K0P, DP> C;
     constexpr int NB = C::NB, NS = C::NS, ROWB0 = C::ROWB0;
     constexpr int TD = TAN ? D + G::NU : 0, RPP = 1 + TD;     // passes per super-tile: primal + one per tangent direction
-    constexpr uint32_t IDESC1 = idesc_f16(TILE_M, TILE_N), IDESC0 = idesc_f16(TILE_M, N0);
+    constexpr uint32_t IDESC1 = idesc_f16(2 * TILE_M, TILE_N), IDESC0 = idesc_f16(2 * TILE_M, N0);   // M = 256 over the CTA pair
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + C::ALIGN_PAD - 1) & ~(uintptr_t)(C::ALIGN_PAD - 1));
@@ -365,7 +140,10 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
     uint64_t* acc1_empty = acc1_full + 2;
     uint64_t* w0_full = acc1_empty + 2;
     uint64_t* w2_full = w0_full + 2;
+    uint64_t* b_peer = w2_full + 2;          // [NB]  leader only: the peer CTA's half of the W1 K-block has landed
+    uint64_t* w0_peer = b_peer + NB;         // [2]   leader only: the peer CTA's half of the layer-0 image has landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBARS);
+    const uint32_t rank = cluster_ctarank();  // 0 = leader (issues every MMA of the pair), 1 = peer
 
     const BnnNet<float>& n = a.net;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -378,7 +156,8 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
     // Each CTA owns a contiguous range of super-tiles; track t takes every other one.  Track 1 is
     // `skew` K-blocks behind track 0 in the W1 stream.
     const long long NT = (long long)P * tiles_p;
-    const long long T0 = NT * blockIdx.x / gridDim.x, T1 = NT * (blockIdx.x + 1) / gridDim.x;
+    const long long ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;       // clusters of two CTAs share a schedule
+    const long long T0 = NT * cid / ncl, T1 = NT * (cid + 1) / ncl;
     const int cnt = (int)(T1 - T0);
     const int ntl[2] = {((cnt + 1) / 2) * RPP, (cnt / 2) * RPP};     // MMA tiles per track
     const int skew = (nkb / 2) & ~1;
@@ -389,35 +168,50 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
 
     if (tid == 0) {
         for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2); }   // both tracks release a W1 stage
-        for (int s = 0; s < 2 * NS; ++s) { mbar_init(&a1_full[s], 128); mbar_init(&a1_empty[s], 1); }
+        for (int s = 0; s < 2 * NS; ++s) { mbar_init(&a1_full[s], 8); mbar_init(&a1_empty[s], 1); }   // one arrival per producer warp of both CTAs
+        for (int s = 0; s < NB; ++s) mbar_init(&b_peer[s], 1);
         for (int t = 0; t < 2; ++t) {
             mbar_init(&acc0_full[t], 1);
-            mbar_init(&acc0_empty[t], 128);
-            mbar_init(&a0_full[t], 128);
+            mbar_init(&acc0_empty[t], 8);
+            mbar_init(&a0_full[t], 8);
             mbar_init(&acc1_full[t], 1);
-            mbar_init(&acc1_empty[t], 128);
+            mbar_init(&acc1_empty[t], 8);
+            mbar_init(&w0_peer[t], 1);
             mbar_init(&w0_full[t], 1);
             mbar_init(&w2_full[t], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync();                            // barriers of both CTAs initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // peer CTA: report the arrival of track t's layer-0 half image to the leader, once per particle change
+    auto w0_relay = [&](int t) {
+        uint32_t loads = 0;
+        int curp = -1;
+        for (int ks = 0; ks * RPP < ntl[t]; ++ks) {
+            const int p = (int)((T0 + 2 * ks + t) / tiles_p);
+            if (p == curp) continue;
+            curp = p;
+            mbar_wait(&w0_full[t], loads & 1);
+            ++loads;
+            mbar_arrive_remote(&w0_peer[t], 0);
+        }
+    };
     if (warp == 18) {
         // ================= loader: W1 K-blocks, shared by both tracks =================
         if (lane == 0) {
             uint32_t s = 0, ph = 1, kb = 0;
             for (int nb = 0; nb < nblk; ++nb) {
                 mbar_wait(&b_empty[s], ph);
-                mbar_expect_tx(&b_full[s], B_STAGE);
-                bulk_g2s(smem + C::B_OFF + s * B_STAGE, im.W1img + (size_t)kb * B_STAGE, B_STAGE, &b_full[s]);
+                mbar_expect_tx(&b_full[s], B_HALF);    // rows [104 rank, 104 rank + 104) of the K-block: this CTA's half of B
+                bulk_g2s(smem + C::B_OFF + s * B_HALF, im.W1img + (size_t)kb * B_STAGE + rank * B_HALF, B_HALF, &b_full[s]);
                 if (++s == NB) { s = 0; ph ^= 1; }
                 if (++kb == (uint32_t)nkb) kb = 0;
             }
@@ -425,7 +219,9 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
     } else if (warp == 19) {
         // ================= layer-0 issuer (one thread, both tracks, polling): chunk c+1 of a track is
         // issued the moment its mid-stage has drained chunk c, independent of where layer 1 stands ====
-        if (lane == 0) {
+        if (lane == 0 && rank != 0) {
+            w0_relay(1);                       // peer: tell the leader when track 1's half image has landed
+        } else if (lane == 0) {
             uint32_t l0cnt[2] = {0, 0}, w0loads[2] = {0, 0};
             int curp[2] = {-1, -1}, k[2] = {0, 0}, pos[2] = {0, 0};
             bool fresh[2] = {true, true};          // next chunk is the first of its tile
@@ -436,14 +232,14 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     if (fresh[t]) {
                         const int p = (int)((T0 + 2 * (k[t] / RPP) + t) / tiles_p);
                         if (p != curp[t]) {
-                            if (!mbar_test(&w0_full[t], w0loads[t] & 1)) continue;
+                            if (!mbar_test(&w0_full[t], w0loads[t] & 1) || !mbar_test_cluster(&w0_peer[t], w0loads[t] & 1)) continue;
                             ++w0loads[t];
                             curp[t] = p;
                         }
-                        if (!mbar_test(&a0_full[t], (uint32_t)k[t] & 1)) continue;
+                        if (!mbar_test_cluster(&a0_full[t], (uint32_t)k[t] & 1)) continue;
                         fresh[t] = false;
                     }
-                    if (!mbar_test(&acc0_empty[t], (l0cnt[t] & 1) ^ 1)) continue;
+                    if (!mbar_test_cluster(&acc0_empty[t], (l0cnt[t] & 1) ^ 1)) continue;
                     tc_fence_after();
                     int kb = t * skew + pos[t];
                     if (kb >= nkb) kb -= nkb;
@@ -454,10 +250,10 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     const uint64_t ad = make_desc<ROWB0>(a0);
                     const uint64_t bx = make_desc<ROWB0>(b0), by = make_desc<ROWB0>(b0 + C::W0_CHUNK_PART);
                     // one K-step = 32 B of a row = 16 fp16: K0P = 8 -> [a0 | a1] in one step; K0P = 16 -> a0, then a1
-                    tc_mma_f16(d_tmem, ad, bx, IDESC0, 0);                          // a0*b0 (+ a1*b0)
-                    if (K0P == 16) tc_mma_f16(d_tmem, ad + 2, bx + 2, IDESC0, 1);   // a1*b0
-                    tc_mma_f16(d_tmem, ad, by, IDESC0, 1);                          // a0*b1
-                    tc_commit(&acc0_full[t]);
+                    tc_mma2_f16(d_tmem, ad, bx, IDESC0, 0);                          // a0*b0 (+ a1*b0)
+                    if (K0P == 16) tc_mma2_f16(d_tmem, ad + 2, bx + 2, IDESC0, 1);   // a1*b0
+                    tc_mma2_f16(d_tmem, ad, by, IDESC0, 1);                          // a0*b1
+                    tc_commit2(&acc0_full[t]);
                     ++l0cnt[t];
                     pos[t] += nk;
                     if (pos[t] >= nkb) { pos[t] = 0; ++k[t]; fresh[t] = true; }
@@ -471,36 +267,52 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
         // registers and feeds UTCHMMA without per-operand R2UR / elect loops: the single-lane version
         // spent ~1000 cycles of dependent scalar code per step for 318 cycles of MMA); one elected lane
         // issues.  Descriptors advance by adding to their low word (address field, 16-byte units).
-        {
+        if (rank != 0) {
+            // peer CTA: these two warps only relay "my half has landed" to the leader (warp 16: W1 K-blocks,
+            // warp 17: track 0's layer-0 image)
+            if (lane == 0) {
+                if (warp == 16) {
+                    uint32_t s = 0, ph = 0;
+                    for (int nb = 0; nb < nblk; ++nb) {
+                        mbar_wait(&b_full[s], ph);
+                        mbar_arrive_remote(&b_peer[s], 0);
+                        if (++s == NB) { s = 0; ph ^= 1; }
+                    }
+                } else {
+                    w0_relay(0);
+                }
+            }
+        } else {
             const int t = __shfl_sync(0xffffffffu, warp, 0) - 16;
             const bool leader = elect_one();
             const int ntiles = t == 0 ? ntl[0] : ntl[1], first_blk = t * skew;
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC1);
             const uint64_t desc_hi = make_desc<64>(0) & 0xFFFFFFFF00000000ull;
             const uint32_t a_lo0 = (uint32_t)make_desc<64>(smem_u32(smem + C::A1_OFF + t * NS * A1_SLOT));
-            const uint32_t b_lo0 = (uint32_t)make_desc<64>(smem_u32(smem + C::B_OFF));
+            const uint32_t b_lo0 = (uint32_t)make_desc<64>(smem_u32(smem + C::B_OFF));   // this CTA's half; the peer's sits at the same offset
             uint64_t* const a1f = a1_full + t * NS;
             uint64_t* const a1e = a1_empty + t * NS;
             uint32_t s = 0, bph = 0, slot = 0, sph = 0;
             int k = 0, pos = 0;
             for (int nb = 0; nb < nblk; ++nb) {
                 mbar_wait(&b_full[s], bph);
+                mbar_wait_cluster(&b_peer[s], bph);
                 if (nb < first_blk || k >= ntiles) {
-                    if (leader) mbar_arrive(&b_empty[s]);   // this track does not use the block
+                    if (leader) { mbar_arrive(&b_empty[s]); mbar_arrive_remote(&b_empty[s], 1); }   // this track does not use the block
                 } else {
-                    if (pos == 0) mbar_wait(&acc1_empty[t], ((uint32_t)k & 1) ^ 1);
-                    mbar_wait(&a1f[slot], sph);
+                    if (pos == 0) mbar_wait_cluster(&acc1_empty[t], ((uint32_t)k & 1) ^ 1);
+                    mbar_wait_cluster(&a1f[slot], sph);
                     tc_fence_after();
                     if (leader) {
                         const uint64_t ad = desc_hi | (uint64_t)(a_lo0 + slot * (A1_SLOT >> 4));
-                        const uint64_t bd = desc_hi | (uint64_t)(b_lo0 + s * (B_STAGE >> 4));
+                        const uint64_t bd = desc_hi | (uint64_t)(b_lo0 + s * (B_HALF >> 4));
                         // one UMMA K-step = 32 B of a row = 16 fp16: [x0 | x1] halves are +2 apart in the >>4 address field
-                        tc_mma_f16(d_tmem, ad, bd, IDESC1, pos != 0);     // a0 * b0
-                        tc_mma_f16(d_tmem, ad, bd + 2, IDESC1, 1);        // a0 * b1
-                        tc_mma_f16(d_tmem, ad + 2, bd, IDESC1, 1);        // a1 * b0
-                        tc_commit(&a1e[slot]);
-                        tc_commit(&b_empty[s]);
-                        if (pos == nkb - 1) tc_commit(&acc1_full[t]);
+                        tc_mma2_f16(d_tmem, ad, bd, IDESC1, pos != 0);     // a0 * b0
+                        tc_mma2_f16(d_tmem, ad, bd + 2, IDESC1, 1);        // a0 * b1
+                        tc_mma2_f16(d_tmem, ad + 2, bd, IDESC1, 1);        // a1 * b0
+                        tc_commit2(&a1e[slot]);
+                        tc_commit2(&b_empty[s]);
+                        if (pos == nkb - 1) tc_commit2(&acc1_full[t]);
                     }
                     __syncwarp();
                     if (++slot == NS) { slot = 0; sph ^= 1; }
@@ -529,7 +341,7 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
             auto fetch = [&](int ks) {         // item r of super-tile ks: particle p, item i -> global row i*P + p
                 const long long tau = T0 + 2 * ks + t;
                 const int p = (int)(tau / tiles_p), l = (int)(tau - (long long)p * tiles_p);
-                const int i = l * TILE_M + r;
+                const int i = l * (2 * TILE_M) + (int)rank * TILE_M + r;    // a pair tile is 256 items, this CTA's half
                 vn = i < S;
 #pragma unroll
                 for (int k = 0; k < K0; ++k) inn[k] = 0.f;
@@ -587,11 +399,14 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     sts128(A0 + swz_byte<ROWB0>(r, 16 * (K0P / 8 + c)), x1[4 * c], x1[4 * c + 1], x1[4 * c + 2], x1[4 * c + 3]);
                 }
                 fence_async_smem();
-                mbar_arrive(&a0_full[t]);
+                warp_arrive_leader(&a0_full[t], rank, lane);
             };
             auto load_w0 = [&](int p) {
                 mbar_expect_tx(&w0_full[t], w0_bytes);
-                bulk_g2s(smem + C::W0_OFF + t * C::W0_BYTES, im.W0img + (size_t)p * C::W0_BYTES, w0_bytes, &w0_full[t]);
+                // the image holds 32-row parts; a CTA feeds rows [16 rank, 16 rank + 16) of every part, which must sit at the
+                // same offset in both CTAs: the peer lands the whole image 16 rows early (its rows 0-15 of a part fall into
+                // the unused upper half of the previous part, or into W0_PAD)
+                bulk_g2s(smem + C::W0_OFF + t * C::W0_BYTES - rank * (16 * ROWB0), im.W0img + (size_t)p * C::W0_BYTES, w0_bytes, &w0_full[t]);
             };
             int curp = (int)((T0 + t) / tiles_p);
             if (r == 0) load_w0(curp);
@@ -617,7 +432,7 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     tc_ld32(lane_taddr + TM_ACC0, v);
                     tc_wait_ld32(v);
                     tc_fence_before();
-                    mbar_arrive(&acc0_empty[t]);
+                    warp_arrive_leader(&acc0_empty[t], rank, lane);
                     if (pos + nk >= nkb && k + 1 < nt) {
                         // every layer-0 MMA of this tile has completed: A0 (and, between super-tiles, the W0 image) is free
                         if (last_pass) {
@@ -669,7 +484,7 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                                 sts128(A1 + (((2 + c) ^ row_sw) << 4), a1[4 * c], a1[4 * c + 1], a1[4 * c + 2], a1[4 * c + 3]);
                             }
                             fence_async_smem();
-                            mbar_arrive(&a1_full[t * NS + slot]);
+                            warp_arrive_leader(&a1_full[t * NS + slot], rank, lane);
                             if (++slot == NS) { slot = 0; sph ^= 1; }
                         }
                     }
@@ -826,7 +641,7 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     if (TAN) push(word);
                 }
                 tc_fence_before();
-                mbar_arrive(&acc1_empty[t]);
+                warp_arrive_leader(&acc1_empty[t], rank, lane);
                 // complete the column sums across the quad, then lane q4 writes outputs o = q4 (and q4 + 4)
 #pragma unroll
                 for (int jr = 0; jr < 4; ++jr)
@@ -843,7 +658,7 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                         const float sd = n.dX_std ? n.dX_std[o] : 1.f, mn = n.dX_mean ? n.dX_mean[o] : 0.f, bo = n.b2[o];
 #pragma unroll
                         for (int jr = 0; jr < 4; ++jr) {
-                            const int i = l * TILE_M + w * 32 + (jr >> 1) * 16 + (jr & 1) * 8 + rq;
+                            const int i = l * (2 * TILE_M) + (int)rank * TILE_M + w * 32 + (jr >> 1) * 16 + (jr & 1) * 8 + rq;
                             if (i < S) {
                                 float yo = 0.f;
 #pragma unroll
@@ -860,11 +675,12 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
         }
     }
 done:
+    __syncwarp();
     tc_fence_before();
-    __syncthreads();
+    cluster_sync();                            // the leader's MMAs read the peer's shared memory and write its TMEM
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
     }
 }
 

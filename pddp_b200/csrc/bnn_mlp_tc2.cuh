@@ -95,9 +95,14 @@ __device__ __forceinline__ void mbar_wait_cluster_fast(uint64_t* bar, uint32_t p
 
 template <int K0P, int DP>
 struct Cfg2 {
-    static constexpr int NB = K0P == 8 ? 7 : 6;    // W1 K-block stages (half blocks: 6.5 KB each)
-    static constexpr int NS = K0P == 8 ? 8 : 6;    // layer-1 A-operand slots per track (deeper than the single-CTA kernel:
-                                                   // the shared memory freed by the half blocks covers the cross-CTA hops)
+    // RES: this CTA's half of the whole W1 image (13 x 6.5 KB) stays RESIDENT in shared memory: no W1 stream, no loader
+    // loop, no b_full / b_empty traffic, and the two tracks no longer advance in lockstep through a shared ring.  Half an
+    // image fits only because cta_group::2 lets each CTA hold half of B; with the 16-wide layer-0 operand (double
+    // cartpole) it does not, and that geometry keeps the ring.  (Measured: -3 % on the rollout launch.  Making the MMA
+    // phases of the two tracks mutually exclusive on top of this changed nothing: see profiles/r1_summary.md section 5.)
+    static constexpr bool RES = K0P == 8;
+    static constexpr int NB = RES ? MAX_NKB : 6;   // resident K-blocks / W1 K-block stages (half blocks: 6.5 KB each)
+    static constexpr int NS = 6;                   // layer-1 A-operand slots per track
     static constexpr int ROWB0 = K0P * 4;
     static constexpr int A0_BYTES = TILE_M * ROWB0;
     static constexpr int W0_CHUNK_PART = N0 * ROWB0, W0_CHUNK = 2 * W0_CHUNK_PART, W0_BYTES = MAX_NCH * W0_CHUNK;
@@ -123,6 +128,7 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
     constexpr int K0P = K0 + 1 <= 8 ? 8 : 16, DP = D <= 4 ? 4 : 8;
     typedef Cfg2<K0P, DP> C;
     constexpr int NB = C::NB, NS = C::NS, ROWB0 = C::ROWB0;
+    constexpr bool RES = C::RES;
     constexpr int TD = TAN ? D + G::NU : 0, RPP = 1 + TD;     // passes per super-tile: primal + one per tangent direction
     constexpr uint32_t IDESC1 = idesc_f16(2 * TILE_M, TILE_N), IDESC0 = idesc_f16(2 * TILE_M, N0);   // M = 256 over the CTA pair
 
@@ -206,7 +212,11 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
     };
     if (warp == 18) {
         // ================= loader: W1 K-blocks, shared by both tracks =================
-        if (lane == 0) {
+        if (lane == 0 && RES) {
+            mbar_expect_tx(&b_full[0], (uint32_t)nkb * B_HALF);       // the whole half image, once
+            for (int kb = 0; kb < nkb; ++kb)
+                bulk_g2s(smem + C::B_OFF + kb * B_HALF, im.W1img + (size_t)kb * B_STAGE + rank * B_HALF, B_HALF, &b_full[0]);
+        } else if (lane == 0) {
             uint32_t s = 0, ph = 1, kb = 0;
             for (int nb = 0; nb < nblk; ++nb) {
                 mbar_wait(&b_empty[s], ph);
@@ -271,7 +281,10 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
             // peer CTA: these two warps only relay "my half has landed" to the leader (warp 16: W1 K-blocks,
             // warp 17: track 0's layer-0 image)
             if (lane == 0) {
-                if (warp == 16) {
+                if (warp == 16 && RES) {
+                    mbar_wait(&b_full[0], 0);
+                    mbar_arrive_remote(&b_peer[0], 0);
+                } else if (warp == 16) {
                     uint32_t s = 0, ph = 0;
                     for (int nb = 0; nb < nblk; ++nb) {
                         mbar_wait(&b_full[s], ph);
@@ -294,6 +307,30 @@ bnn_mlp_tc2_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_
             uint64_t* const a1e = a1_empty + t * NS;
             uint32_t s = 0, bph = 0, slot = 0, sph = 0;
             int k = 0, pos = 0;
+            if (RES) {
+                mbar_wait(&b_full[0], 0);
+                mbar_wait_cluster(&b_peer[0], 0);
+                for (k = 0; k < ntiles; ++k) {
+                    mbar_wait_cluster(&acc1_empty[t], ((uint32_t)k & 1) ^ 1);
+                    for (pos = 0; pos < nkb; ++pos) {
+                        int kb = first_blk + pos;
+                        if (kb >= nkb) kb -= nkb;
+                        mbar_wait_cluster(&a1f[slot], sph);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint64_t ad = desc_hi | (uint64_t)(a_lo0 + slot * (A1_SLOT >> 4));
+                            const uint64_t bd = desc_hi | (uint64_t)(b_lo0 + (uint32_t)kb * (B_HALF >> 4));
+                            tc_mma2_f16(d_tmem, ad, bd, IDESC1, pos != 0);     // a0 * b0
+                            tc_mma2_f16(d_tmem, ad, bd + 2, IDESC1, 1);        // a0 * b1
+                            tc_mma2_f16(d_tmem, ad + 2, bd, IDESC1, 1);        // a1 * b0
+                            tc_commit2(&a1e[slot]);
+                            if (pos == nkb - 1) tc_commit2(&acc1_full[t]);
+                        }
+                        __syncwarp();
+                        if (++slot == NS) { slot = 0; sph ^= 1; }
+                    }
+                }
+            } else
             for (int nb = 0; nb < nblk; ++nb) {
                 mbar_wait(&b_full[s], bph);
                 mbar_wait_cluster(&b_peer[s], bph);

@@ -367,15 +367,16 @@ def main():
         achieved = flops / (pms[dom] / pcnt[dom] * 1e-3) / 1e12
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
         # (profiles/r1_summary.md, default workload only; null for the others)
-        traffic = {1: 37.1e6 + 3.4e6, 0: 4.6e6 + 0.2e6}[dom] if args.workload == "cartpole_bnn_b4096" else None
+        traffic = {1: 36.7e6 + 3.0e6, 0: 4.6e6 + 0.2e6}[dom] if args.workload == "cartpole_bnn_b4096" else None
         roofline = {"bound": "tensor", "kernel": ["bnn_mlp (linearise rows)", "bnn_mlp (rollout rows)"][dom],
                     "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                     "traffic": traffic, "peak_source": "bf16 dense sustained, " + peak_src,
                     "tensor_passes_per_product": 3,
                     "frac_of_fp32_accurate_bound": 3.0 * achieved / tensor_peak,
                     "note": "fp32-accurate products on the tensor core cost 3 FP16 passes (a0*b0 + a0*b1 + a1*b0), "
-                            "so `frac` of the 16-bit dense peak cannot exceed 1/3; the kernel itself is bound by "
-                            "the shared-memory data pipe (profiles/r1_summary.md)",
+                            "so `frac` of the 16-bit dense peak cannot exceed 1/3; tensor pipe 63 % active, shared-memory "
+                            "data pipe 98 %, and the tile's layer-0 -> mid-stage -> layer-1 -> epilogue dependency chain "
+                            "plus the 1 kW power cap set the time (profiles/r1_summary.md section 5)",
                     "flops_per_launch": flops, "avg_launch_ms": pms[dom] / pcnt[dom],
                     "mlp_share_of_step": (pms[0] + pms[1]) / (ms / args.steps), "kernels": kinds}
     else:

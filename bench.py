@@ -39,10 +39,13 @@ WORKLOADS = {
     "cartpole_bnn_mpc_b8192": dict(problem="cartpole", enc=1, B=8192, N=50, P=50, A=16, hidden=200, umax=10.0),
     "pendulum_known_b1m": dict(problem="pendulum", enc=4, B=1 << 20, N=100, P=0, A=10, hidden=0, umax=2.5),
     "cartpole_bnn_small": dict(problem="cartpole", enc=1, B=64, N=10, P=50, A=10, hidden=200, umax=10.0),
+    # action_size 4 (Jacobi eigen-clipping + 4-dimensional box QP in the backward pass)
+    "rendezvous_known_b64k": dict(problem="rendezvous", enc=4, B=1 << 16, N=100, P=0, A=10, hidden=0, umax=1.0),
 }
 GEOMETRY = {"pendulum": (0, 2, (0,), (1,)), "cartpole": (1, 4, (2,), (0, 1, 3)),
-            "double_cartpole": (2, 6, (2, 4), (0, 1, 3, 5))}
-KNOWN_PARAMS = {"pendulum": [0.1, 1.0, 1.0, 0.1, 9.80665]}
+            "double_cartpole": (2, 6, (2, 4), (0, 1, 3, 5)), "rendezvous": (3, 8, (), tuple(range(8)))}
+KNOWN_PARAMS = {"pendulum": [0.1, 1.0, 1.0, 0.1, 9.80665], "rendezvous": [0.1, 1.0, 0.1]}
+ACTION_SIZE = {"rendezvous": 4}
 
 
 def cost_constants(problem, dtype=torch.float64):
@@ -58,6 +61,10 @@ def cost_constants(problem, dtype=torch.float64):
         Q[3, 3] = Q[4, 4] = .25
         return Q, 0.1 * torch.eye(1, dtype=dtype), torch.eye(5, dtype=dtype), torch.tensor(
             [0, 0, 0, math.sin(math.pi), math.cos(math.pi)], dtype=dtype)
+    if problem == "rendezvous":            # pddp/examples/rendezvous/cost.py:29-43
+        Q = torch.eye(8, dtype=dtype)
+        Q[0, 2] = Q[2, 0] = Q[1, 3] = Q[3, 1] = -1
+        return Q, 0.1 * torch.eye(4, dtype=dtype), Q.clone(), torch.zeros(8, dtype=dtype)
     C = torch.tensor([[1, -.6, 0, -.6, 0], [0, 0, .6, 0, .6]], dtype=dtype)
     Q = torch.zeros(8, 8, dtype=dtype)
     dims = [0, 4, 5, 6, 7]
@@ -97,6 +104,8 @@ def synth_inputs(w, seed, dtype):
     start = torch.zeros(D)
     if w["problem"] == "double_cartpole":
         start[2] = start[4] = math.pi
+    if w["problem"] == "rendezvous":       # pddp/examples/rendezvous/env.py:106-108
+        start = torch.tensor([-10.0, -10.0, 10.0, 10.0, 0.0, -5.0, 5.0, 0.0])
     mean = start + 1e-2 * torch.randn(w["B"], D, generator=g)
     if w["enc"] == 4:
         z0 = mean
@@ -105,7 +114,7 @@ def synth_inputs(w, seed, dtype):
         z0 = torch.cat([mean, (0.1 * torch.eye(D))[iu[0], iu[1]].expand(w["B"], -1)], -1)
     else:
         z0 = torch.cat([mean, (1e-2 * torch.eye(D)).reshape(-1).expand(w["B"], -1)], -1)
-    U = 0.1 * torch.randn(w["B"], w["N"], 1, generator=g)
+    U = 0.1 * torch.randn(w["B"], w["N"], ACTION_SIZE.get(w["problem"], 1), generator=g)
     return z0.to(dtype).contiguous(), U.to(dtype).contiguous()
 
 
@@ -168,12 +177,12 @@ def oracle_problem(w, dtype, n_problems, seed):
     import pddp_oracle as O
     geo, D, ang, nonang = GEOMETRY[w["problem"]]
     Q, R, Qt, goal = cost_constants(w["problem"], dtype)
-    cost = O.QRCostSpec(Q, R, Qt, goal, torch.zeros(1, dtype=dtype), D, ang, nonang)
+    cost = O.QRCostSpec(Q, R, Qt, goal, torch.zeros(ACTION_SIZE.get(w["problem"], 1), dtype=dtype), D, ang, nonang)
     if w["P"]:
         W, b, masks, eps0 = synth_bnn(w["problem"], w["P"], w["hidden"], seed)
         dyn = O.BNNSpec(list(zip(W, b)), masks, eps0, D, 1, ang, nonang).to(dtype)
     else:
-        dyn = O.pendulum_spec(*KNOWN_PARAMS["pendulum"])
+        dyn = {"pendulum": O.pendulum_spec, "rendezvous": O.rendezvous_spec}[w["problem"]](*KNOWN_PARAMS[w["problem"]])
     z0, U = synth_inputs(dict(w, B=max(n_problems, 1)), seed + 1, dtype)
     return O, dyn, cost, z0, U
 
@@ -182,7 +191,8 @@ def time_oracle(w, dtype, n_problems, seed=0):
     """Seconds for `n_problems` sequential problem-iterations of the reference algorithm on the
     host cores (the reference optimises one problem at a time, SURVEY.md section 2 note)."""
     O, dyn, cost, z0, U = oracle_problem(w, dtype, n_problems, seed)
-    lo, hi = torch.tensor([-w["umax"]], dtype=dtype), torch.tensor([w["umax"]], dtype=dtype)
+    nu = ACTION_SIZE.get(w["problem"], 1)
+    lo, hi = torch.full((nu,), -w["umax"], dtype=dtype), torch.full((nu,), w["umax"], dtype=dtype)
     alphas = O.fit_alphas(dtype, w["A"])
     t0 = time.perf_counter()
     for i in range(n_problems):
@@ -273,7 +283,8 @@ def main():
     solver = BatchedSolver(dyn, cost, w["enc"], w["B"], w["N"], dtype=dtype, device=dev, max_alphas=w["A"])
     z0_h, U_h = synth_inputs(w, seed=1 + rank, dtype=dtype)
     z0_h, U_h = z0_h.pin_memory(), U_h.pin_memory()
-    lo, hi = [-w["umax"]], [w["umax"]]
+    nu = ACTION_SIZE.get(w["problem"], 1)
+    lo, hi = [-w["umax"]] * nu, [w["umax"]] * nu
     alphas = (1.025 ** (-torch.arange(float(w["A"]), dtype=torch.float64) ** 2)).to(dtype)
     solver.set_problem(z0_h.to(dev), U_h.to(dev), lo, hi, alphas=alphas, iterations=1 << 30)
 
@@ -380,9 +391,9 @@ def main():
                     "flops_per_launch": flops, "avg_launch_ms": pms[dom] / pcnt[dom],
                     "mlp_share_of_step": (pms[0] + pms[1]) / (ms / args.steps), "kernels": kinds}
     else:
-        nz = solver.nz
-        elems = 2 * nz * nz + 2 * nz + 2 * nz + 1 + 1 + 1 + 1 + (2 * nz * nz + 2 * nz + nz + 2 + 1 + nz) + (
-            nz + 2 + nz) + (nz + 1)
+        nz, nu = solver.nz, solver.nu      # linearise writes + backward reads/writes + rollout reads/writes
+        elems = (2 * nz * nz + 2 * nz * nu + 2 * nz + nu + nu * nu + 1 + nu) + (
+            2 * nz * nz + 2 * nz * nu + nz + nu + nu * nu + nu + nu * nz) + (nz + 2 * nu + nu * nz) + (nz + nu)
         bytes_per_step = elems * (4 if dtype == torch.float32 else 8) * w["B"] * w["N"]
         achieved = bytes_per_step / (ms / args.steps * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "whole pass (linearise+backward+rollout+accept)", "achieved": achieved,

@@ -183,12 +183,16 @@ int pddp_rollout_known(const pddp_shape* shape, const pddp_known_dynamics* dyn,
  *          active[b]: 0 = finished, 1 = needs a fresh linearisation, 2 = retry backward+rollout
  *          on the existing linearisation with the increased mu (ilqr.py:213-233)
  *   out  : accepted[B] (1 where the candidate was taken), n_active[1] int32 incremented by the
- *          number of problems that still need passes (may be NULL)                              */
+ *          number of problems that still need passes (may be NULL)
+ *   K, K_nominal (both or neither, [B,N,nu*nz]): the gains of THIS backward pass are copied into
+ *          K_nominal only where the candidate was accepted -- the reference stores self._K on an accepted
+ *          step only (ilqr.py:166-171), so after a fit that ends in MAX_REG the feedback law still uses
+ *          the gains of the last accepted step, not those of the rejected high-mu retries.           */
 int pddp_accept_update(const pddp_shape* shape, const void* J_new, const int32_t* bw_status,
                        const void* Z_new, const void* U_new, double tol, double max_reg, double* mu,
                        double* delta, void* J_opt, int32_t* state, int32_t* iters_left,
                        int32_t* active, void* Z, void* U, int32_t* accepted, int32_t* n_active,
-                       void* stream);
+                       const void* K, void* K_nominal, void* stream);
 
 /* ---- BNN dynamics ----------------------------------------------------------------------------
  * pddp_linearize_bnn replaces ilqr.forward with a factory-built BNNDynamicsModel
@@ -226,6 +230,40 @@ int pddp_cost_derivatives(const pddp_shape* shape, const pddp_cost* cost, const 
  *   out: x_next[B, D]  (may alias x)                                                                  */
 int pddp_env_step_known(const pddp_shape* shape, const pddp_known_dynamics* dyn, const void* x, const void* u,
                         void* x_next, void* stream);
+
+/* ---- BNN training on the device -------------------------------------------------
+ * Replaces the optimisation loop of ParticlesBNNDynamicsModel.fit (pddp/models/bnn/modules.py:174-198):
+ * n_iter steps of torch.optim.Adam(amsgrad=True) on
+ *     -gaussian_log_likelihood(dX, mean, exp(log_std)).mean() + reg_scale * model.regularization() / n_data
+ * (pddp/models/bnn/losses.py:20-38; regulariser modules.py:434-447, 517-530, 749-766: drop_0 weighs fc_1,
+ * drop_1 weighs fc_out, with keep-probability 1 - rate: the learned logit_p never reaches it, see
+ * csrc/bnn_train.cu), the network evaluated in training mode with
+ * a fresh dropout mask per (row, unit) and step (modules.py:462-483, 550-583, resample=True).
+ *   params  flat [W0[H0,K0] | b0[H0] | W1[H1,H0] | b1[H1] | W2[2D,H1] | b2[2D] | logit_p0 | logit_p1]
+ *           (torch layouts; logit_p only for dropout == 0), updated in place
+ *   X [n_data,K0] augmented state + action (un-normalised), dX [n_data,D] targets; X_mean / X_std_inv [K0],
+ *   dX_mean / dX_std [D] normalisation buffers or NULL pairs (0 / 1)
+ *   batch_idx [n_iter,batch] int32 rows of the step's mini-batch, -1 = empty slot (partial last batch)
+ *   noise   [n_iter,batch,H0+H1] uniforms for the masks, or NULL: counter-based generator from cfg.seed
+ *   grads   gradient of the LAST step (same layout as params), loss [n_iter] the loss of every step        */
+typedef struct pddp_bnn_train_config {
+    int32_t dtype;                 /* PDDP_F32 | PDDP_F64 */
+    int32_t K0, H0, H1, D;         /* input width DA+nu, hidden widths, state size (output width 2D) */
+    int32_t n_data, batch, n_iter;
+    int32_t dropout;               /* 0 = CDropout (concrete, learns logit_p), 1 = BDropout (Bernoulli(1-rate)) */
+    double lr, beta1, beta2, eps;  /* Adam */
+    double reg_scale, temperature;
+    double reg0, reg1;             /* BDropout.reg of drop_0 / drop_1 */
+    double rate0, rate1;           /* BDropout.rate of drop_0 / drop_1 (both kinds: the regulariser uses 1 - rate) */
+    uint64_t seed;
+} pddp_bnn_train_config;
+
+int64_t pddp_bnn_train_workspace_bytes(const pddp_bnn_train_config* cfg);
+
+int pddp_bnn_train(const pddp_bnn_train_config* cfg, const void* X, const void* dX, const void* X_mean,
+                   const void* X_std_inv, const void* dX_mean, const void* dX_std, const int32_t* batch_idx,
+                   const void* noise, void* params, void* grads, void* loss, void* workspace,
+                   int64_t workspace_bytes, void* stream);
 
 /* ---- instrumentation (bench.py) -----------------------------------------------------------------
  * pddp_profile_enable(1) makes the BNN path bracket its kernels with CUDA events on the launch

@@ -783,3 +783,78 @@ class ILQR:
             if state in (CONVERGED, MAX_REG):
                 break
         return self.Z, self.U, state
+
+
+# --------------------------------------------------------------------------------------
+# BNN training (ref: models/bnn/modules.py:131-198 fit loop, 434-447 / 517-530 / 749-766 regulariser,
+# models/bnn/losses.py:20-38 likelihood).  Restated with explicit forward / backward formulas (no autograd)
+# so that it documents exactly what the device trainer computes; pinned by tests/golden/train_*.npz, which the
+# reference's own fit() produced (oracle/make_golden_train.py).
+# --------------------------------------------------------------------------------------
+def bnn_train(p, X_, dX, batch_idx, noise, hidden, D, dropout, lr, reg_scale, reg=1.0, rate=0.5, temperature=0.1,
+              X_mean=None, X_std_inv=None, dX_mean=None, dX_std=None, betas=(0.9, 0.999), eps=1e-8):
+    """p: flat [W0|b0|W1|b1|W2|b2|logit_p0|logit_p1]; X_: [n, K0] augmented state + action; batch_idx [T, bs]
+    (-1 = empty); noise [T, bs, H0+H1] uniforms.  Returns (p_final, grads of step 0, loss of every step)."""
+    H0, H1 = hidden
+    K0, OUT, n = X_.shape[1], 2 * D, X_.shape[0]
+    sizes = [H0 * K0, H0, H1 * H0, H1, OUT * H1, OUT, 1, 1]
+    p = p.clone()
+    m, v, vmax = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    losses, grads0 = [], None
+    for it in range(batch_idx.shape[0]):
+        W0, b0, W1, b1, W2, b2, lp0, lp1 = [t.reshape(s) for t, s in zip(
+            p.split(sizes), [(H0, K0), (H0,), (H1, H0), (H1,), (OUT, H1), (OUT,), (), ()])]
+        rows = batch_idx[it]
+        live = rows >= 0
+        rows, r = rows[live].long(), noise[it][live]
+        nb = rows.numel()
+        a0 = X_[rows] if X_mean is None else (X_[rows] - X_mean) * X_std_inv
+        if dropout == 0:
+            keep = [torch.sigmoid(lp0), torch.sigmoid(lp1)]
+            mk = lambda u, lp: torch.sigmoid((lp + u.log() - (1 - u).log()) / temperature)
+            m0, m1 = mk(r[:, :H0], lp0), mk(r[:, H0:], lp1)
+        else:
+            keep = [torch.tensor(1 - rate, dtype=p.dtype)] * 2
+            m0, m1 = (r[:, :H0] < keep[0]).to(p.dtype), (r[:, H0:] < keep[1]).to(p.dtype)
+        pre0 = a0 @ W0.T + b0
+        h0 = torch.relu(pre0 * m0)
+        pre1 = h0 @ W1.T + b1
+        h1 = torch.relu(pre1 * m1)
+        out = h1 @ W2.T + b2
+        sc = torch.ones(D, dtype=p.dtype) if dX_std is None else dX_std
+        sh = torch.zeros(D, dtype=p.dtype) if dX_mean is None else dX_mean
+        mean, log_std = out[:, :D] * sc + sh, out[:, D:] + sc.log()
+        q = (mean - dX[rows]) * (-log_std).exp()
+        nll = 0.5 * (q ** 2).sum(-1) + log_std.sum(-1) + 0.5 * math.log(2 * math.pi)
+        # the regulariser's keep-probability is ALWAYS 1 - rate: CDropout.regularization sets p.data = sigmoid(logit_p)
+        # and then calls BDropout.regularization, whose first statement rebinds self.p = 1 - self.rate
+        # (modules.py:443, 526-527), so the learned logit_p never reaches it
+        pr = torch.tensor(1 - rate, dtype=p.dtype)
+        regv = reg * (pr * (W1 ** 2).sum() + (b1 ** 2).sum()) + reg * (pr * (W2 ** 2).sum() + (b2 ** 2).sum())
+        if dropout == 0:
+            regv = regv - 2 * (-(1 - pr) * (1 - pr).log() - pr * pr.log())
+        losses.append(nll.mean() + reg_scale * regv / n)
+        # backward
+        dout = torch.cat([q * (-log_std).exp() * sc, 1 - q ** 2], -1) / nb
+        dz1 = (dout @ W2) * (pre1 * m1 > 0)
+        dp1 = dz1 * m1
+        dz0 = (dp1 @ W1) * (pre0 * m0 > 0)
+        dp0 = dz0 * m0
+        rs = reg_scale / n
+        g = [dp0.T @ a0, dp0.sum(0), dp1.T @ h0 + rs * reg * pr * 2 * W1, dp1.sum(0) + rs * reg * 2 * b1,
+             dout.T @ h1 + rs * reg * pr * 2 * W2, dout.sum(0) + rs * reg * 2 * b2]
+        if dropout == 0:
+            g += [(dz0 * pre0 * m0 * (1 - m0) / temperature).sum().reshape(1), (dz1 * pre1 * m1 * (1 - m1) / temperature).sum().reshape(1)]
+        else:
+            g += [torch.zeros(1, dtype=p.dtype)] * 2
+        g = torch.cat([t.reshape(-1) for t in g])
+        if grads0 is None:
+            grads0 = g.clone()
+        m = betas[0] * m + (1 - betas[0]) * g
+        v = betas[1] * v + (1 - betas[1]) * g * g
+        vmax = torch.maximum(vmax, v)
+        step = (lr / (1 - betas[0] ** (it + 1))) * m / (vmax.sqrt() / math.sqrt(1 - betas[1] ** (it + 1)) + eps)
+        if dropout != 0:
+            step[-2:] = 0
+        p = p - step
+    return p, grads0, torch.stack(losses)

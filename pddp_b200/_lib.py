@@ -55,13 +55,15 @@ _SIGNATURES = {
     "pddp_rollout_known": (C.c_int, [C.POINTER(Shape), C.POINTER(KnownDynamics), C.POINTER(Cost)]
                            + [_P] * 5 + [C.c_int32] + [_P] * 10),
     "pddp_accept_update": (C.c_int, [C.POINTER(Shape)] + [_P] * 4 + [C.c_double, C.c_double]
-                           + [_P] * 11),
+                           + [_P] * 13),
     "pddp_cost_derivatives": (C.c_int, [C.POINTER(Shape), C.POINTER(Cost)] + [_P] * 11),
     "pddp_bnn_workspace_bytes": (C.c_int64, [C.POINTER(Shape), C.POINTER(BNN), C.c_int32]),
     "pddp_linearize_bnn": (C.c_int, [C.POINTER(Shape), C.POINTER(BNN), C.POINTER(Cost)] + [_P] * 16
                            + [_P, C.c_int64, _P]),
     "pddp_rollout_bnn": (C.c_int, [C.POINTER(Shape), C.POINTER(BNN), C.POINTER(Cost)] + [_P] * 5
                          + [C.c_int32] + [_P] * 10 + [_P, C.c_int64, _P]),
+    "pddp_bnn_train_workspace_bytes": (C.c_int64, [_P]),
+    "pddp_bnn_train": (C.c_int, [_P] * 12 + [_P, C.c_int64, _P]),
     "pddp_env_step_known": (C.c_int, [C.POINTER(Shape), C.POINTER(KnownDynamics)] + [_P] * 4),
     "pddp_profile_enable": (None, [C.c_int]),
     "pddp_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

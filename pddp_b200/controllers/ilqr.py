@@ -1,22 +1,23 @@
-"""iLQR / PDDP controllers: the reference's controller API on top of the batched GPU solver.
+"""iLQR controller: the reference's controller API on top of the batched GPU solver.
 
-Same class names, constructor / `fit` / `step` / `forward` signatures, callbacks, return values and
-`iLQRState` enum as pddp/controllers/{base,ilqr,pddp}.py, so a script written against the reference
-keeps working; additionally `U` may carry a leading problem dimension ([B, N, nu] with z0 [B, nz])
-and then B independent problems are optimised together, each with its own regularisation state.
+Same class name, constructor / `fit` / `step` / `forward` signatures, callbacks, return values and `iLQRState`
+enum as pddp/controllers/ilqr.py, so a script written against the reference keeps working; additionally `U` may
+carry a leading problem dimension ([B, N, nu] with z0 [B, nz]) and then B independent problems are optimised
+together, each with its own regularisation state -- and, under `torchrun`, split across the GPUs of the job.
 
-The module-level functions `forward`, `Q`, `backward`, `_control_law`, `_trajectory_cost` keep the
-reference signatures (single problem, time-major tensors) and call the same kernels with B = 1.
+The module-level functions `forward`, `Q`, `backward`, `_control_law`, `_trajectory_cost` keep the reference
+signatures (single problem, time-major tensors) and call the same kernels with B = 1 on cached buffers.
 """
 import warnings
 from enum import IntEnum
 
 import torch
 
-from . import _lib
-from .encoding import StateEncoding, decode_mean
-from .models import check_model_opts
-from .solver import LIN_NAMES, BatchedSolver, fit_alphas, step_alphas
+from .. import _lib, sharding
+from ..models.bnn.modules import check_model_opts
+from ..solver import LIN_NAMES, cached_solver, expand_bound, fit_alphas, step_alphas
+from ..utils.encoding import StateEncoding, decode_mean
+from .base import Controller
 
 
 class iLQRState(IntEnum):
@@ -33,23 +34,6 @@ class iLQRState(IntEnum):
 
     def is_terminal(self):
         return self in (iLQRState.CONVERGED, iLQRState.MAX_REG)
-
-
-class Controller(torch.nn.Module):
-    """ref: pddp/controllers/base.py:21-71"""
-
-    def fit(self, U, encoding=StateEncoding.DEFAULT, **kwargs):
-        raise NotImplementedError
-
-    def forward(self, z, i, encoding=StateEncoding.DEFAULT, **kwargs):
-        raise NotImplementedError
-
-
-def _solver_for(model, cost, encoding, B, N, dtype, device, max_alphas=16, model_opts={}):
-    desc = model.descriptor(model_opts, N) if getattr(model, "is_bnn", False) else model.descriptor()
-    if cost.geometry() != desc.geo:
-        raise ValueError("model and cost disagree on the state geometry")
-    return BatchedSolver(desc, cost.constants(), encoding, B, N, dtype=dtype, device=device, max_alphas=max_alphas)
 
 
 def _bounds(u_min, u_max):
@@ -79,16 +63,25 @@ class iLQRController(Controller):
     def _delta(self):
         return 2.0 if self._solver is None else float(self._solver.delta[0])
 
+    def invalidate(self):
+        """Drops the device buffers (and the device copies of the model they captured)."""
+        self._solver = None
+
     def _get_solver(self, B, N, encoding, dtype, device, n_alphas):
-        s = self._solver
-        if (s is None or (s.B, s.N, int(s.enc), s.dtype, s.device) != (B, N, int(encoding), dtype, device)
-                or s.max_alphas < n_alphas):
-            self._solver = _solver_for(self.model, self.cost, encoding, B, N, dtype, device, max(16, n_alphas),
-                                       self._model_opts)
-        return self._solver
+        """Buffers for this problem shape.  The cache is keyed on the model's `_version` (bumped by
+        resample / fit / load_reference), and the cost / closed-form model constants are re-read on every call,
+        so an edited model or cost is never served from stale device copies."""
+        s = cached_solver(self.model, self.cost, encoding, B, N, dtype, device, max_alphas=max(16, n_alphas),
+                          model_opts=self._model_opts)
+        if s is not self._solver:
+            s.view("K_nominal").zero_()
+        self._solver = s
+        return s
 
     def _results(self, s):
-        Z, U, K = s.view("Z").clone(), s.view("U").clone(), s.matrices("K").clone()
+        """Nominal trajectory, controls and the gains of the last ACCEPTED step (ref: ilqr.py:166-171: `_K` is
+        only stored on acceptance; K_nominal is written by pddp_accept_update where accepted[b] is set)."""
+        Z, U, K = s.view("Z").clone(), s.view("U").clone(), s.matrices("K_nominal").clone()
         if self._batched:
             self._Z_nominal, self._U_nominal, self._K = Z, U, K
             return Z, U, s.state.clone()
@@ -98,7 +91,8 @@ class iLQRController(Controller):
     def step(self, z0, U=None, i=0, encoding=StateEncoding.DEFAULT, batch_rollout=True, alphas=None, u_min=None,
              u_max=None, on_iteration=None, tol=5e-6, max_reg=1e10, _keep_reg=True, **kwargs):
         """One optimisation step: linearise once, then retry backward + rollout with a larger
-        regularisation while the state is NOT_PD / REJECTED (ref: ilqr.py:183-235)."""
+        regularisation while the state is NOT_PD / REJECTED (ref: ilqr.py:183-235).  `batch_rollout` is accepted
+        for signature compatibility: the kernels always evaluate every alpha and every tangent in parallel."""
         if U is None:
             U = self._U_nominal
         _lib.require_cuda(U, "U")
@@ -109,7 +103,7 @@ class iLQRController(Controller):
         u_min, u_max = _bounds(u_min, u_max)
         s = self._get_solver(Ub.shape[0], Ub.shape[1], encoding, U.dtype, U.device, int(alphas.numel()))
         mu, delta = s.mu.clone(), s.delta.clone()
-        s.set_problem(zb.to(U.dtype), Ub, u_min, u_max, alphas=alphas, iterations=1)
+        s.set_problem(zb.to(device=U.device, dtype=U.dtype), Ub, u_min, u_max, alphas=alphas, iterations=1)
         if _keep_reg:            # regularisation persists across steps of one fit (ilqr.py:277 resets per fit)
             s.mu.copy_(mu)
             s.delta.copy_(delta)
@@ -126,9 +120,14 @@ class iLQRController(Controller):
         return s.state.clone() if self._batched else iLQRState(int(s.state[0]))
 
     def fit(self, U, encoding=StateEncoding.DEFAULT, n_iterations=50, tol=5e-6, max_reg=1e10, batch_rollout=True,
-            quiet=False, on_iteration=None, u_min=None, u_max=None, z0=None, **kwargs):
+            quiet=False, on_iteration=None, u_min=None, u_max=None, z0=None, shard=None, **kwargs):
         """ref: pddp/controllers/ilqr.py:237-316.  U: [N, nu] (z0 read from env.get_state() unless
-        given) or [B, N, nu] with z0 [B, nz].  Returns (Z, U, state)."""
+        given) or [B, N, nu] with z0 [B, nz].  Returns (Z, U, state).
+
+        Multi-GPU: with torch.distributed initialised (one process per GPU under torchrun) and a
+        batched call, every rank passes the SAME full batch; each optimises its contiguous share of the problems
+        -- no collective inside the iteration -- and ONE all-gather at the end gives every rank the full
+        (Z, U, K, state).  shard=False keeps the whole batch on this rank."""
         _lib.require_cuda(U, "U")
         self._batched = U.dim() == 3
         Ub = (U if self._batched else U.unsqueeze(0)).detach()
@@ -136,6 +135,11 @@ class iLQRController(Controller):
             z0 = self.env.get_state().encode(encoding).detach()
         zb = z0.to(device=U.device, dtype=U.dtype).reshape(Ub.shape[0], -1)
         u_min, u_max = _bounds(u_min, u_max)
+        world, rank = sharding.world_and_rank()
+        sharded = self._batched and world > 1 and shard is not False and Ub.shape[0] >= world
+        B_total = Ub.shape[0]
+        if sharded:
+            Ub, zb = sharding.shard(Ub, world, rank).contiguous(), sharding.shard(zb, world, rank).contiguous()
         s = self._get_solver(Ub.shape[0], Ub.shape[1], encoding, U.dtype, U.device, 10)
         it = [0]
 
@@ -154,7 +158,12 @@ class iLQRController(Controller):
               alphas=fit_alphas(U.dtype), on_pass=on_pass)
         if bool((s.state == int(iLQRState.MAX_REG)).any()):
             warnings.warn("exceeded max regularization term")
-        return self._results(s)
+        if not sharded:
+            return self._results(s)
+        Z, Uo, K, state = sharding.all_gather_problems(
+            [s.view("Z").contiguous(), s.view("U").contiguous(), s.matrices("K_nominal").contiguous(), s.state], B_total)
+        self._Z_nominal, self._U_nominal, self._K = Z, Uo, K
+        return Z, Uo, state
 
     def forward(self, z, i, encoding=StateEncoding.DEFAULT, mpc=False, ignore_uncertainty=True, u_min=None,
                 u_max=None, **kwargs):
@@ -168,6 +177,7 @@ class iLQRController(Controller):
                 return Un
             Zn = self._Z_nominal[:, i] if self._batched else self._Z_nominal[i]
             Kn = self._K[:, i] if self._batched else self._K[i]
+            z = z.to(Zn.device)
             if ignore_uncertainty:
                 D = self.model.state_size
                 dx = decode_mean(z, encoding, D) - decode_mean(Zn, encoding, D)
@@ -183,92 +193,6 @@ class iLQRController(Controller):
         return u
 
 
-class PDDPController(iLQRController):
-    """ref: pddp/controllers/pddp.py:32-206.  The trial loop (collect data with the controller on the
-    env, retrain the model) is host-side and unchanged in spirit; every `super().fit()` inside it
-    is the GPU hot path."""
-
-    def __init__(self, env, model, cost, model_opts={}, cost_opts={}, training_opts={}, **kwargs):
-        super().__init__(env, model, cost, model_opts, cost_opts, **kwargs)
-        self._training_opts = training_opts
-
-    def fit(self, U, encoding=StateEncoding.DEFAULT, quiet=False, on_trial=None, max_trials=None,
-            n_initial_sample_trajectories=2, sampling_noise=1.0, train_on_start=True, max_dataset_size=1000,
-            resample_model=True, u_min=None, u_max=None, **kwargs):
-        U = U.detach()
-        dataset, total_trials = None, 0
-        if train_on_start:
-            for i in range(n_initial_sample_trajectories):
-                self.env.reset()
-                Ui = U if i == 0 else sampling_noise * torch.rand_like(U)
-                if i > 0 and u_min is not None and u_max is not None:
-                    Ui = (u_max - u_min) * Ui + u_min
-                new_data, _ = _apply_controller(self.env, self.cost, Ui, U.shape[0], encoding, False, quiet,
-                                                self._cost_opts, u_min=u_min, u_max=u_max)
-                dataset = _concat_datasets(dataset, new_data, max_dataset_size)
-                if callable(on_trial):
-                    on_trial(total_trials, new_data[0], new_data[1])
-                total_trials += 1
-            self.model.train()
-            self.model.fit(*[t.cpu() for t in dataset], quiet=quiet, **self._training_opts)
-        while True:
-            self.env.reset()
-            self.model.eval()
-            if resample_model and hasattr(self.model, "resample"):
-                self.model.resample()
-            self._solver = None                       # new weights / masks -> new device copies
-            Z, U, state = super().fit(U, encoding=encoding, quiet=quiet, u_min=u_min, u_max=u_max, **kwargs)
-            if not self.training:
-                break
-            new_data, _ = _apply_controller(self.env, self.cost, self, 2 * U.shape[0], encoding, True, quiet,
-                                            self._cost_opts, u_min=u_min, u_max=u_max, **kwargs)
-            if callable(on_trial):
-                on_trial(total_trials, new_data[0], new_data[1])
-            dataset = _concat_datasets(dataset, new_data, max_dataset_size)
-            self.model.train()
-            self.model.fit(*[t.cpu() for t in dataset], quiet=quiet, **self._training_opts)
-            total_trials += 1
-            if max_trials is not None and total_trials >= max_trials:
-                break
-        return Z, U, state
-
-
-def _apply_controller(env, cost, controller, H, encoding, mpc=False, quiet=False, cost_opts={}, **kwargs):
-    """ref: pddp/controllers/pddp.py:209-247 -> ((X, U, dX), J): runs `controller` (a feedback / MPC
-    controller, or a tensor of open-loop controls) on `env` for H steps and returns the trial's dataset
-    and cost.  With a device environment (pddp_b200.envs) nothing leaves the GPU: the simulator step is
-    `pddp_env_step_known`, every MPC step is one batched iteration of the hot path, and B instances
-    ([B, nz] states, [B, nu] actions) run at once; the dataset is then [B*H, ...] and J is [B]."""
-    Z, U = [], []
-    open_loop = controller if isinstance(controller, torch.Tensor) else None
-    dev = open_loop.device if open_loop is not None else controller._U_nominal.device
-    for i in range(H):
-        z = env.get_state().encode(encoding).to(dev)
-        Z.append(z)
-        if open_loop is not None:
-            u = open_loop[:, i] if open_loop.dim() == 3 else open_loop[i]
-        else:
-            u = controller(z, i, encoding, mpc, **kwargs)
-        U.append(u)
-        env.apply(u)
-    Z.append(env.get_state().encode(encoding).to(dev))
-    Z, U = torch.stack(Z).detach(), torch.stack(U).detach()          # [H+1, (B,) nz], [H, (B,) nu]
-    J = _trajectory_cost(cost, Z, U, encoding, cost_opts) if Z.is_cuda else None
-    X = decode_mean(Z, encoding, getattr(env, "state_size", None))
-    X, dX = X[:-1], X[1:] - X[:-1]
-    if Z.dim() == 3:                                                 # instance-major rows, like B trials back to back
-        X, U, dX = (t.transpose(0, 1).reshape(-1, t.shape[-1]) for t in (X, U, dX))
-    return (X, U, dX), J
-
-
-def _concat_datasets(first, second, max_dataset_size=None):
-    """ref: pddp/controllers/pddp.py:250-267"""
-    if first is None:
-        return second
-    out = tuple(torch.cat([a, b]) for a, b in zip(first, second))
-    return tuple(t[-max_dataset_size:] for t in out) if max_dataset_size is not None else out
-
-
 # ---------------------------------------------------------------------------------------------
 # module-level functions with the reference signatures (single problem, B = 1)
 # ---------------------------------------------------------------------------------------------
@@ -278,8 +202,8 @@ def forward(z0, U, model, cost, encoding=StateEncoding.DEFAULT, batch_rollout=Tr
     check_model_opts(model, model_opts)
     _lib.require_cuda(U, "U")
     u_min, u_max = _bounds(u_min, u_max)
-    s = _solver_for(model, cost, encoding, 1, U.shape[0], U.dtype, U.device, model_opts=model_opts)
-    s.set_problem(z0.reshape(1, -1).to(U.dtype), U.unsqueeze(0), u_min, u_max)
+    s = cached_solver(model, cost, encoding, 1, U.shape[0], U.dtype, U.device, model_opts=model_opts)
+    s.set_problem(z0.reshape(1, -1).to(device=U.device, dtype=U.dtype), U.unsqueeze(0), u_min, u_max)
     s.linearize(use_active=False)
     return tuple(s.matrices(n)[0].clone() for n in LIN_NAMES)
 
@@ -326,17 +250,18 @@ class _RawBackward:
     def run(self, F_z, F_u, L_z, L_u, L_zz, L_uz, L_uu, reg, U, u_min, u_max):
         import ctypes as C
         lib, p = _lib.load(), _lib.ptr
-        c = lambda t: t.to(self.dtype).contiguous()
+        c = lambda t: t.detach().to(self.dtype).contiguous()
         o = dict(dtype=self.dtype, device=self.device)
         k, K = torch.zeros(self.N, self.nu, **o), torch.zeros(self.N, self.nu, self.nz, **o)
         mu = torch.full((1,), float(reg), dtype=torch.float64, device=self.device)
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
         args = [c(t) for t in (F_z, F_u, L_z, L_u, L_zz, L_uz, L_uu)]
         Uc = None if U is None else c(U)
-        lo = None if u_min is None else c(torch.as_tensor(u_min).reshape(-1).to(self.device))
-        hi = None if u_max is None else c(torch.as_tensor(u_max).reshape(-1).to(self.device))
-        _lib.check(lib.pddp_backward(C.byref(self.shape), *[p(t) for t in args], p(mu), p(Uc), p(lo), p(hi), None,
-                                     p(k), p(K), p(status), _lib.stream_ptr()), "backward")
+        lo = expand_bound(u_min, self.nu, self.dtype, self.device)     # the reference broadcasts a 1-element bound
+        hi = expand_bound(u_max, self.nu, self.dtype, self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.pddp_backward(C.byref(self.shape), *[p(t) for t in args], p(mu), p(Uc), p(lo), p(hi), None,
+                                         p(k), p(K), p(status), _lib.stream_ptr()), "backward")
         return k, K, int(status.item())
 
 
@@ -344,22 +269,19 @@ class _RawBackward:
 def _control_law(model, Z, U, k, K, alpha, encoding=StateEncoding.DEFAULT, model_opts={}, u_min=None, u_max=None,
                  cost=None):
     """ref: pddp/controllers/ilqr.py:677-723 -> (Z_new [N+1, A, nz], U_new [N, A, nu]) for every
-    alpha (the fused kernel only keeps the winner, so this convenience wrapper rolls each alpha
-    separately)."""
+    alpha (the fused kernel only keeps the winner's trajectory, so this reference-shaped wrapper rolls the A
+    candidates as A problems of a batch with one alpha each)."""
     check_model_opts(model, model_opts)
-    from .costs import QRCost
     u_min, u_max = _bounds(u_min, u_max)
-    DA = model.state_size + len(model.angular_indices)
-    cost = cost or QRCost(torch.zeros(DA, DA), torch.zeros(int(model.action_size), int(model.action_size)),
-                          state_size=model.state_size,
-                          angular_indices=model.angular_indices.tolist())
-    s = _solver_for(model, cost, encoding, 1, U.shape[0], U.dtype, U.device, model_opts=model_opts)
+    alpha = torch.as_tensor(alpha).reshape(-1)
+    s = cached_solver(model, cost, encoding, 1, U.shape[0], U.dtype, U.device, model_opts=model_opts)
     Zs, Us = [], []
-    for a in alpha.reshape(-1):
-        s.set_problem(Z[0].reshape(1, -1), U.unsqueeze(0), u_min, u_max, alphas=a.reshape(1))
-        s.store("Z", Z.unsqueeze(0))
-        s.store("k", k.unsqueeze(0))
-        s.store("K", K.reshape(1, K.shape[0], -1))
+    s.set_problem(Z[0].reshape(1, -1), U.unsqueeze(0), u_min, u_max, alphas=alpha[:1])
+    s.store("Z", Z.detach().unsqueeze(0))
+    s.store("k", k.detach().unsqueeze(0))
+    s.store("K", K.detach().reshape(1, K.shape[0], -1))
+    for a in alpha:
+        s.alphas.copy_(a.reshape(1))
         s.rollout(use_active=False, use_bw_status=False)
         Zs.append(s.view("Z_new")[0].clone())
         Us.append(s.view("U_new")[0].clone())
@@ -374,11 +296,13 @@ def _trajectory_cost(cost, Z, U, encoding=StateEncoding.DEFAULT, cost_opts={}):
     batched = Z.dim() == 3
     Zb = Z.permute(1, 0, 2) if batched else Z.unsqueeze(0)
     Ub = U.permute(1, 0, 2) if batched else U.unsqueeze(0)
-    from .solver import KnownDynamics
-    s = BatchedSolver(KnownDynamics(cost.geometry(), [0.0] * 8), cost.constants(), encoding, Zb.shape[0], Ub.shape[1],
-                      dtype=Z.dtype, device=Z.device, layout=_lib.PROBLEM_MAJOR)
-    s.store("Z", Zb)
-    s.store("U", Ub)
+    s = cached_solver(None, cost, encoding, Zb.shape[0], Ub.shape[1], Z.dtype, Z.device, layout=_lib.PROBLEM_MAJOR)
+    s.store("Z", Zb.detach())
+    s.store("U", Ub.detach())
     s.cost_only()
     J = s.J_opt.clone()
     return J if batched else J[0]
+
+
+__all__ = ["iLQRController", "iLQRState", "StateEncoding", "forward", "Q", "backward", "_control_law",
+           "_trajectory_cost"]

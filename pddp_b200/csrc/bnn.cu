@@ -15,7 +15,6 @@
 #include "bnn_common.cuh"
 #include "bnn_mlp_simt.cuh"
 #include "bnn_mlp_tc.cuh"
-#include "bnn_mlp_tc2.cuh"
 #include "kernels.h"
 #include "profile.h"
 #include <stdio.h>
@@ -559,42 +558,6 @@ static cudaError_t launch_mlp_tc(const BnnMlpArgs<float>& a, const tc::Images& i
     kern<<<grid, tc::THREADS, smem, st>>>(a, im, S, tiles_p, (a.net.H0 + 1 + tc::KB - 1) / tc::KB);
     return cudaGetLastError();
 }
-// CTA-pair version (bnn_mlp_tc2.cuh): clusters of two CTAs, 256-item tiles.  PDDP_MLP_2CTA=0 selects the single-CTA kernel.
-static bool use_cta_pairs() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("PDDP_MLP_2CTA"); on = (e && e[0] == '1') ? 1 : 0; }
-    return on == 1;
-}
-template <int GEO, bool TAN>
-static cudaError_t launch_mlp_tc2(const BnnMlpArgs<float>& a, const tc::Images& im, cudaStream_t st) {
-    typedef Geo<GEO> G;
-    constexpr int K0P = G::DA + G::NU + 1 <= 8 ? 8 : 16, DP = G::D <= 4 ? 4 : 8;
-    auto kern = tc::bnn_mlp_tc2_kernel<GEO, TAN>;
-    const int smem = tc::Cfg2<K0P, DP>::TOTAL + tc::Cfg2<K0P, DP>::ALIGN_PAD;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    const int S = (int)(a.total / a.net.P);
-    const int tiles_p = (S + 2 * tc::TILE_M - 1) / (2 * tc::TILE_M);     // pair super-tiles per particle
-    const long long ntiles = (long long)tiles_p * a.net.P;
-    // a persistent grid must be co-resident: not every TPC of a floor-swept part has both SMs, so ask how many
-    // CTA pairs fit (74 clusters on 148 SMs ran in two waves: exactly 2x the time)
-    static int max_clusters = 0;
-    if (max_clusters == 0) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(num_sms() & ~1); cfg.blockDim = dim3(tc::THREADS); cfg.dynamicSmemBytes = smem;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
-        max_clusters = n;
-        if (getenv("PDDP_DEBUG")) fprintf(stderr, "pddp_b200: %d CTA pairs co-resident on %d SMs\n", n, num_sms());
-    }
-    const long long ncl = ntiles < (long long)max_clusters ? ntiles : (long long)max_clusters;
-    kern<<<(int)(2 * ncl), tc::THREADS, smem, st>>>(a, im, S, tiles_p, (a.net.H0 + 1 + tc::KB - 1) / tc::KB);
-    return cudaGetLastError();
-}
 template <class T, int GEO, bool TAN>
 static cudaError_t launch_mlp(const BnnMlpArgs<T>& a, const tc::Images& im, cudaStream_t st) {
     const int H = a.net.H0 > a.net.H1 ? a.net.H0 : a.net.H1;
@@ -605,7 +568,7 @@ static cudaError_t launch_mlp(const BnnMlpArgs<T>& a, const tc::Images& im, cuda
         return cudaErrorInvalidValue;
     }
     if (use_tensor_cores<T>(a.net.H0, a.net.H1)) {
-        if constexpr (sizeof(T) == 4) return use_cta_pairs() ? launch_mlp_tc2<GEO, TAN>(a, im, st) : launch_mlp_tc<GEO, TAN>(a, im, st);
+        if constexpr (sizeof(T) == 4) return launch_mlp_tc<GEO, TAN>(a, im, st);
     }
     if (H <= 32) return launch_mlp_simt<T, GEO, TAN, 2>(a, st);
     if (H <= 208) return launch_mlp_simt<T, GEO, TAN, 13>(a, st);

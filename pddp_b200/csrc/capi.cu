@@ -220,7 +220,7 @@ template <class T>
 static int accept_t(const pddp_shape* s, const void* J_new, const int32_t* bw_status, const void* Z_new,
                     const void* U_new, double tol, double max_reg, double* mu, double* delta, void* J_opt,
                     int32_t* state, int32_t* iters_left, int32_t* active, void* Z, void* U,
-                    int32_t* accepted, int32_t* n_active, cudaStream_t st) {
+                    int32_t* accepted, int32_t* n_active, const void* K, void* K_nominal, cudaStream_t st) {
     AcceptArgs<T> a;
     a.B = s->B; a.N = s->N; a.nz = s->nz; a.nu = s->nu;
     a.J_new = (const T*)J_new; a.bw_status = bw_status; a.Z_new = (const T*)Z_new; a.U_new = (const T*)U_new;
@@ -228,6 +228,8 @@ static int accept_t(const pddp_shape* s, const void* J_new, const int32_t* bw_st
     a.iters_left = iters_left; a.active = active; a.Z = (T*)Z; a.U = (T*)U; a.n_active = n_active;
     a.lZ = make_layout(s->layout, s->B, s->N + 1, s->nz);
     a.lU = make_layout(s->layout, s->B, s->N, s->nu);
+    a.K = (const T*)K; a.K_nominal = (T*)K_nominal;
+    a.lK = make_layout(s->layout, s->B, s->N, s->nu * s->nz);
     note_launches(2);
     return cuda_result(accept_update<T>(a, accepted, st), "pddp_accept_update");
 }
@@ -236,14 +238,16 @@ extern "C" int pddp_accept_update(const pddp_shape* s, const void* J_new, const 
                                   const void* Z_new, const void* U_new, double tol, double max_reg,
                                   double* mu, double* delta, void* J_opt, int32_t* state,
                                   int32_t* iters_left, int32_t* active, void* Z, void* U,
-                                  int32_t* accepted, int32_t* n_active, void* stream) {
+                                  int32_t* accepted, int32_t* n_active, const void* K, void* K_nominal,
+                                  void* stream) {
     if (int e = check_shape(s)) return e;
     if (!J_new || !Z_new || !U_new || !mu || !delta || !J_opt || !state || !iters_left || !active || !Z || !U || !accepted)
         return fail(PDDP_E_BADARG, "pddp_accept_update: NULL argument");
+    if ((K == nullptr) != (K_nominal == nullptr)) return fail(PDDP_E_BADARG, "pddp_accept_update: K and K_nominal go together");
     cudaStream_t st = (cudaStream_t)stream;
     if (s->dtype == PDDP_F32)
-        return accept_t<float>(s, J_new, bw_status, Z_new, U_new, tol, max_reg, mu, delta, J_opt, state, iters_left, active, Z, U, accepted, n_active, st);
-    return accept_t<double>(s, J_new, bw_status, Z_new, U_new, tol, max_reg, mu, delta, J_opt, state, iters_left, active, Z, U, accepted, n_active, st);
+        return accept_t<float>(s, J_new, bw_status, Z_new, U_new, tol, max_reg, mu, delta, J_opt, state, iters_left, active, Z, U, accepted, n_active, K, K_nominal, st);
+    return accept_t<double>(s, J_new, bw_status, Z_new, U_new, tol, max_reg, mu, delta, J_opt, state, iters_left, active, Z, U, accepted, n_active, K, K_nominal, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -43,7 +43,8 @@ struct AcceptArgs {
     double tol, max_reg;
     double* mu; double* delta; T* J_opt; int32_t* state; int32_t* iters_left; int32_t* active;
     T* Z; T* U; int32_t* n_active;
-    Layout lZ, lU;
+    const T* K; T* K_nominal;      // optional: gains kept only for accepted steps (ilqr.py:166-171)
+    Layout lZ, lU, lK;
 };
 
 template <class T>

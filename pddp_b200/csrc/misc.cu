@@ -58,7 +58,8 @@ __global__ void accept_state_kernel(const AcceptArgs<T> a, int32_t* accepted) {
 // copy the accepted candidates into the nominal trajectory (self._Z_nominal/_U_nominal)
 template <class T>
 __global__ void accept_copy_kernel(const AcceptArgs<T> a, const int32_t* accepted) {
-    const int64_t per = (int64_t)(a.N + 1) * a.nz + (int64_t)a.N * a.nu;
+    const int64_t nK = a.K_nominal ? (int64_t)a.N * a.nu * a.nz : 0;
+    const int64_t per = (int64_t)(a.N + 1) * a.nz + (int64_t)a.N * a.nu + nK;
     const int64_t total = per * a.B;
     for (int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; id < total;
          id += (int64_t)gridDim.x * blockDim.x) {
@@ -71,10 +72,13 @@ __global__ void accept_copy_kernel(const AcceptArgs<T> a, const int32_t* accepte
         if (slot < (int64_t)(a.N + 1) * a.nz) {
             int64_t t = slot / a.nz, e = slot % a.nz;
             a.Z[a.lZ.at(b, t, e)] = a.Z_new[a.lZ.at(b, t, e)];
-        } else {
-            slot -= (int64_t)(a.N + 1) * a.nz;
+        } else if ((slot -= (int64_t)(a.N + 1) * a.nz) < (int64_t)a.N * a.nu) {
             int64_t t = slot / a.nu, e = slot % a.nu;
             a.U[a.lU.at(b, t, e)] = a.U_new[a.lU.at(b, t, e)];
+        } else {
+            slot -= (int64_t)a.N * a.nu;
+            const int64_t E = (int64_t)a.nu * a.nz, t = slot / E, e = slot % E;
+            a.K_nominal[a.lK.at(b, t, e)] = a.K[a.lK.at(b, t, e)];
         }
     }
 }
@@ -82,7 +86,8 @@ __global__ void accept_copy_kernel(const AcceptArgs<T> a, const int32_t* accepte
 template <class T>
 cudaError_t accept_update(const AcceptArgs<T>& a, int32_t* accepted_scratch, cudaStream_t s) {
     accept_state_kernel<T><<<(a.B + 127) / 128, 128, 0, s>>>(a, accepted_scratch);
-    const int64_t total = ((int64_t)(a.N + 1) * a.nz + (int64_t)a.N * a.nu) * a.B;
+    const int64_t total = ((int64_t)(a.N + 1) * a.nz + (int64_t)a.N * a.nu +
+                           (a.K_nominal ? (int64_t)a.N * a.nu * a.nz : 0)) * a.B;
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     accept_copy_kernel<T><<<grid, 256, 0, s>>>(a, accepted_scratch);
@@ -101,14 +106,21 @@ template cudaError_t accept_update<double>(const AcceptArgs<double>&, int32_t*, 
 // (it also carries the gradient), pairs inside {means, C[ang][ang]}, and C[ang_i][*] / C[*][ang_i] against
 // {m_ang_i, C[ang_i][ang_i]} -- then the rest, which only get zeros written (double cartpole: 119 of 903
 // pairs are evaluated).  Entry = i * 256 + j.
+// __constant__ memory is PER DEVICE: the table is uploaded once per (device, geometry), the pair count is
+// device independent.
 __constant__ uint16_t c_pair_order[3][1024];
 static int g_pair_nnz[3] = {-1, -1, -1};
+static bool g_pair_uploaded[64][3] = {};
 
 template <int GEO>
 static cudaError_t fill_pair_order(int* nnz_out) {
     typedef Geo<GEO> G;
     constexpr int D = G::D, NZ = D + D * D;
-    if (g_pair_nnz[GEO] >= 0) { *nnz_out = g_pair_nnz[GEO]; return cudaSuccess; }
+    int dev = 0;
+    cudaError_t de = cudaGetDevice(&dev);
+    if (de != cudaSuccess) return de;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (g_pair_uploaded[dev][GEO]) { *nnz_out = g_pair_nnz[GEO]; return cudaSuccess; }
     auto is_ang = [](int a) { for (int i = 0; i < G::NANG; ++i) if (G::ang(i) == a) return true; return false; };
     // class of a variable: 0 mean, 1 C[ang][ang], 2 C with exactly one angular index, 3 C[nonang][nonang]
     auto cls = [&](int v, int& angle) {
@@ -133,7 +145,8 @@ static cudaError_t fill_pair_order(int* nnz_out) {
                 if (pass == 0 && i == NZ - 1 && j == NZ - 1) g_pair_nnz[GEO] = n;
             }
     cudaError_t e = cudaMemcpyToSymbol(c_pair_order, order, sizeof(uint16_t) * n, sizeof(uint16_t) * 1024 * GEO);
-    if (e != cudaSuccess) { g_pair_nnz[GEO] = -1; return e; }
+    if (e != cudaSuccess) return e;
+    g_pair_uploaded[dev][GEO] = true;
     *nnz_out = g_pair_nnz[GEO];
     return cudaSuccess;
 }

@@ -1,4 +1,4 @@
-"""Environments (mirror of pddp/envs/base.py + pddp/envs/gym_env.py and the example envs), batched and
+"""Environments (mirror of pddp/envs/base.py + pddp/envs/gym_env.py), batched and
 device resident: B independent instances of a problem whose ground truth is one of the closed-form
 dynamics models, stepped by `pddp_env_step_known` so that a closed-loop MPC run or a data-collection
 trial (pddp/controllers/pddp.py:209-247, `_apply_controller`) never leaves the GPU.
@@ -9,14 +9,18 @@ import ctypes as C
 
 import torch
 
-from . import _lib
-from .encoding import GaussianVariable
-from .models import (CartpoleDynamicsModel, DoubleCartpoleDynamicsModel, PendulumDynamicsModel,
-                     RendezvousDynamicsModel)
+from .. import _lib
+from ..utils.gaussian_variable import GaussianVariable
 
 
 class Env(object):
-    """ref: pddp/envs/base.py:21-68"""
+    """ref: pddp/envs/base.py:21-75"""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, type, value, traceback):
+        self.close()
 
     @property
     def action_size(self):
@@ -47,7 +51,9 @@ class KnownDynamicsEnv(Env):
     initial_state = None      # mean of reset()
     reset_noise = 1e-2        # ref: examples/*/env.py reset(): state += 1e-2 * randn
 
-    def __init__(self, model, batch_size=None, dtype=torch.float32, device="cuda", generator=None):
+    def __init__(self, model, batch_size=None, dtype=torch.float32, device="cuda", generator=None, render=False):
+        if render:
+            raise NotImplementedError("pddp_b200 environments are device-resident simulators without rendering")
         self.model = model
         self.batch_size = batch_size
         self.dtype, self.device = dtype, torch.device(device)
@@ -89,8 +95,10 @@ class KnownDynamicsEnv(Env):
         state in float32 whatever the default dtype (`x = self.state.astype(np.float32)`); so does this."""
         u = torch.as_tensor(u).detach().to(device=self.device, dtype=self.dtype).reshape(self._state.shape[0], -1).contiguous()
         x = self._state.float().to(self.dtype)
-        _lib.check(_lib.load().pddp_env_step_known(C.byref(self._shape), C.byref(self._c_dyn), _lib.ptr(x), _lib.ptr(u),
-                                                   _lib.ptr(self._state), _lib.stream_ptr()), "env_step_known")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().pddp_env_step_known(C.byref(self._shape), C.byref(self._c_dyn), _lib.ptr(x),
+                                                       _lib.ptr(u), _lib.ptr(self._state), _lib.stream_ptr()),
+                       "env_step_known")
 
     def get_state(self, var=1e-2):
         """ref: pddp/envs/gym_env.py:75-85"""
@@ -98,38 +106,6 @@ class KnownDynamicsEnv(Env):
         return GaussianVariable(mean, var=var * torch.ones_like(mean))
 
     def reset(self):
-        x0 = torch.as_tensor(self.initial_state, dtype=torch.float64)
-        noise = torch.randn(self._state.shape, dtype=torch.float64, generator=self._generator)
+        x0 = torch.tensor(self.initial_state, dtype=torch.float64, device="cpu")
+        noise = torch.randn(self._state.shape, dtype=torch.float64, generator=self._generator, device="cpu")
         self._state.copy_((x0 + self.reset_noise * noise).to(self.dtype))
-
-
-class PendulumEnv(KnownDynamicsEnv):
-    """ref: pddp/examples/pendulum/env.py:30-113"""
-    initial_state = [0.0, 0.0]
-
-    def __init__(self, dt=0.1, **kwargs):
-        super().__init__(PendulumDynamicsModel(dt), **kwargs)
-
-
-class CartpoleEnv(KnownDynamicsEnv):
-    """ref: pddp/examples/cartpole/env.py:30-118"""
-    initial_state = [0.0, 0.0, 0.0, 0.0]
-
-    def __init__(self, dt=0.1, **kwargs):
-        super().__init__(CartpoleDynamicsModel(dt), **kwargs)
-
-
-class DoubleCartpoleEnv(KnownDynamicsEnv):
-    """ref: pddp/examples/double_cartpole/env.py:30-117"""
-    initial_state = [0.0, 0.0, 3.141592653589793, 0.0, 3.141592653589793, 0.0]
-
-    def __init__(self, dt=0.1, **kwargs):
-        super().__init__(DoubleCartpoleDynamicsModel(dt), **kwargs)
-
-
-class RendezvousEnv(KnownDynamicsEnv):
-    """ref: pddp/examples/rendezvous/env.py:30-108"""
-    initial_state = [-10.0, -10.0, 10.0, 10.0, 0.0, -5.0, 5.0, 0.0]
-
-    def __init__(self, dt=0.1, **kwargs):
-        super().__init__(RendezvousDynamicsModel(dt), **kwargs)

@@ -7,14 +7,38 @@ pass), marshals pointers into the C ABI and never touches the data itself.  Ther
 ref: pddp/controllers/ilqr.py:102-316 (what one problem's `step`/`fit` do; here vectorised over B
 with per-problem mu/delta/state, SURVEY.md section 5 "failure detection" row).
 """
+import collections
 import ctypes as C
+import functools
+import weakref
 
 import torch
 
 from . import _lib
-from .encoding import StateEncoding, infer_encoded_state_size
+from .utils.encoding import StateEncoding, infer_encoded_state_size
 
 LIN_NAMES = ("Z", "F_z", "F_u", "L", "L_z", "L_u", "L_zz", "L_uz", "L_uu")
+
+
+def on_own_device(method):
+    """Runs a method with the object's device current: the C ABI launches on the CURRENT device and
+    torch.cuda.current_stream() is per device, so a solver on cuda:1 must not launch on cuda:0."""
+    @functools.wraps(method)
+    def wrapped(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapped
+
+
+def expand_bound(u, nu, dtype, device):
+    """u_min / u_max as the kernels read them: a contiguous [nu] vector.  The reference broadcasts a
+    scalar or 1-element bound in clamp() and in `u_min - U[i]` (ilqr.py:461-462, 649-651)."""
+    if u is None:
+        return None
+    u = torch.as_tensor(u, dtype=dtype).reshape(-1)
+    if u.numel() not in (1, nu):
+        raise ValueError("control bounds must have 1 or action_size=%d elements, got %d" % (nu, u.numel()))
+    return u.expand(nu).to(device).contiguous()
 
 
 def fit_alphas(dtype=torch.float32, device=None, n=10):
@@ -153,7 +177,7 @@ class BatchedSolver:
         nz, nu, N = self.nz, self.nu, self.N
         dims = dict(Z=(N + 1, nz), F_z=(N, nz * nz), F_u=(N, nz * nu), L=(N + 1, 1), L_z=(N + 1, nz),
                     L_u=(N, nu), L_zz=(N + 1, nz * nz), L_uz=(N, nu * nz), L_uu=(N, nu * nu),
-                    U=(N, nu), k=(N, nu), K=(N, nu * nz), Z_new=(N + 1, nz), U_new=(N, nu))
+                    U=(N, nu), k=(N, nu), K=(N, nu * nz), K_nominal=(N, nu * nz), Z_new=(N + 1, nz), U_new=(N, nu))
         self.buf = {n: self._alloc(nt, e) for n, (nt, e) in dims.items()}
         o = dict(device=self.device)
         self.z0 = torch.zeros(self.B, nz, dtype=dtype, **o)
@@ -209,7 +233,7 @@ class BatchedSolver:
         v = self.view(name)
         nz, nu = self.nz, self.nu
         shapes = dict(F_z=(nz, nz), F_u=(nz, nu), L_zz=(nz, nz), L_uz=(nu, nz), L_uu=(nu, nu),
-                      K=(nu, nz))
+                      K=(nu, nz), K_nominal=(nu, nz))
         if name in shapes:
             return v.reshape(v.shape[0], v.shape[1], *shapes[name])
         if name == "L":
@@ -218,16 +242,14 @@ class BatchedSolver:
 
     # ---------------------------------------------------------------- setup
     def set_problem(self, z0, U, u_min=None, u_max=None, alphas=None, iterations=1):
-        z0 = torch.as_tensor(z0)
+        z0 = torch.as_tensor(z0).detach()
         _lib.require_cuda(z0, "z0")
         self.z0.copy_(z0.reshape(self.B, self.nz))
-        self.store("U", torch.as_tensor(U))
+        self.store("U", torch.as_tensor(U).detach())
         if (u_min is None) != (u_max is None):
             raise ValueError("u_min and u_max must be given together")
-        self.u_min = None if u_min is None else torch.as_tensor(u_min, dtype=self.dtype).reshape(
-            -1).to(self.device).contiguous()
-        self.u_max = None if u_max is None else torch.as_tensor(u_max, dtype=self.dtype).reshape(
-            -1).to(self.device).contiguous()
+        self.u_min = expand_bound(u_min, self.nu, self.dtype, self.device)
+        self.u_max = expand_bound(u_max, self.nu, self.dtype, self.device)
         if alphas is not None:
             self.alphas = torch.as_tensor(alphas).to(dtype=self.dtype, device=self.device).contiguous()
         if self.alphas.numel() > self.max_alphas:
@@ -245,6 +267,7 @@ class BatchedSolver:
         self.active.fill_(1)
 
     # ---------------------------------------------------------------- the four stages
+    @on_own_device
     def linearize(self, use_active=True):
         b, p = self.buf, _lib.ptr
         act = p(self.active) if use_active else None
@@ -262,6 +285,7 @@ class BatchedSolver:
                 p(self.lin_status), _lib.stream_ptr())
             _lib.check(code, "linearize_known")
 
+    @on_own_device
     def cost_only(self):
         """Cost value / gradient / Hessian of whatever is stored in Z, U (no rollout)."""
         b, p = self.buf, _lib.ptr
@@ -270,6 +294,7 @@ class BatchedSolver:
             p(b["L_u"]), p(b["L_zz"]), p(b["L_uz"]), p(b["L_uu"]), p(self.J_opt), _lib.stream_ptr())
         _lib.check(code, "cost_derivatives")
 
+    @on_own_device
     def backward(self, use_active=True):
         b, p = self.buf, _lib.ptr
         code = self.lib.pddp_backward(
@@ -279,6 +304,7 @@ class BatchedSolver:
             _lib.stream_ptr())
         _lib.check(code, "backward")
 
+    @on_own_device
     def rollout(self, use_active=True, use_bw_status=True):
         b, p = self.buf, _lib.ptr
         A = int(self.alphas.numel())
@@ -296,6 +322,7 @@ class BatchedSolver:
                                                C.byref(self.c_cost), *common, _lib.stream_ptr())
             _lib.check(code, "rollout_known")
 
+    @on_own_device
     def accept(self, tol=5e-6, max_reg=1e10):
         b, p = self.buf, _lib.ptr
         self.n_active.zero_()
@@ -303,7 +330,7 @@ class BatchedSolver:
             C.byref(self.shape), p(self.J_new), p(self.bw_status), p(b["Z_new"]), p(b["U_new"]),
             float(tol), float(max_reg), p(self.mu), p(self.delta), p(self.J_opt), p(self.state),
             p(self.iters_left), p(self.active), p(b["Z"]), p(b["U"]), p(self.accepted),
-            p(self.n_active), _lib.stream_ptr())
+            p(self.n_active), p(b["K"]), p(b["K_nominal"]), _lib.stream_ptr())
         _lib.check(code, "accept_update")
 
     def iterate(self, tol=5e-6, max_reg=1e10):
@@ -331,3 +358,63 @@ class BatchedSolver:
             if int(self.n_active.item()) == 0:     # one 4-byte D2H read per pass
                 break
         return self.view("Z"), self.view("U"), self.state
+
+
+# ---------------------------------------------------------------------------------------------
+# Solver cache for the reference-shaped entry points (module-level forward / _control_law /
+# _trajectory_cost, model(z, u, i), cost(z, u, i), utils.evaluation.*): the reference calls these once
+# per time step or per iteration, so buffers, BNN device copies and tensor-core weight images must not
+# be rebuilt per call.  Small LRU keyed on the objects and shapes; cheap host constants (cost matrices,
+# closed-form model parameters) are re-read on every hit, BNN weights are tracked by `model._version`.
+# ---------------------------------------------------------------------------------------------
+_SOLVER_CACHE = collections.OrderedDict()
+_SOLVER_CACHE_SIZE = 6
+
+
+def _zero_cost(geo):
+    D, nu, ang, _ = _lib.GEO_INFO[geo]
+    DA = D + len(ang)
+    return QRCostConstants(torch.zeros(DA, DA), torch.zeros(nu, nu), torch.zeros(DA, DA), torch.zeros(DA))
+
+
+def cached_solver(model, cost, encoding, B, N, dtype, device, max_alphas=16, model_opts=None, layout=None):
+    """BatchedSolver for (model, cost) -- either may be None: a cost-only solver (pddp_cost_derivatives) or a
+    model-only one with a zero cost (model forward / eval_dynamics)."""
+    if model is None and cost is None:
+        raise ValueError("cached_solver needs a model or a cost")
+    opts = tuple(sorted((model_opts or {}).items()))
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (id(model), getattr(model, "_version", 0), id(cost), int(encoding), int(B), int(N), dtype, str(device),
+           layout, opts)
+    hit = _SOLVER_CACHE.get(key)
+    if hit is not None and hit[0]() is model and hit[1]() is cost and hit[2].max_alphas >= max_alphas:
+        _SOLVER_CACHE.move_to_end(key)
+        s = hit[2]
+    else:
+        is_bnn = getattr(model, "is_bnn", False)
+        if model is None:
+            desc = KnownDynamics(cost.geometry(), [0.0] * 8)
+        else:
+            desc = model.descriptor(dict(opts), N) if is_bnn else model.descriptor()
+        if cost is not None and model is not None and cost.geometry() != desc.geo:
+            raise ValueError("model and cost disagree on the state geometry")
+        consts = cost.constants() if cost is not None else _zero_cost(desc.geo)
+        s = BatchedSolver(desc, consts, encoding, B, N, dtype=dtype, device=device, layout=layout,
+                          max_alphas=max(16, max_alphas))
+        ref = lambda o: (lambda: None) if o is None else weakref.ref(o)
+        _SOLVER_CACHE[key] = (ref(model), ref(cost), s)
+        while len(_SOLVER_CACHE) > _SOLVER_CACHE_SIZE:
+            _SOLVER_CACHE.popitem(last=False)
+        return s
+    if cost is not None:                                  # live constants, like the reference's live objects
+        s.c_cost = cost.constants().c_struct()
+    if model is not None and not s.dyn.is_bnn:
+        s.dyn = model.descriptor()
+        s.c_dyn = s.dyn.c_struct()
+    return s
+
+
+def clear_solver_cache():
+    _SOLVER_CACHE.clear()

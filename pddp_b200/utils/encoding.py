@@ -39,6 +39,11 @@ def infer_state_size(encoded_state_size, encoding=StateEncoding.DEFAULT):
     raise ValueError("no state size encodes to %d under %r" % (encoded_state_size, encoding))
 
 
+def _cholesky(C, jitter=1e-12, max_jitter=10.0):
+    """ref: pddp/utils/encoding.py:536-564 (same name as the reference's helper)"""
+    return _jittered_cholesky_upper(C, jitter, max_jitter)
+
+
 def _jittered_cholesky_upper(C, jitter=1e-12, max_jitter=10.0):
     """U with U^T U = C + jitter I, jitter escalating x10 (ref: pddp/utils/encoding.py:536-564)."""
     eye = torch.eye(C.shape[-1], dtype=C.dtype, device=C.device)
@@ -101,15 +106,29 @@ def decode_var(Z, encoding=StateEncoding.DEFAULT, state_size=None):
     return torch.diagonal(decode_covar(Z, encoding, state_size), dim1=-2, dim2=-1)
 
 
-class GaussianVariable:
-    """Minimal stand-in for pddp.utils.gaussian_variable.GaussianVariable: what `env.get_state()`
-    returns and the controller encodes (ref: pddp/envs/gym_env.py:75-85, controllers/ilqr.py:285)."""
+def decode_std(Z, encoding=StateEncoding.DEFAULT, state_size=None):
+    """Standard deviations [..., D] (IGNORE_UNCERTAINTY: the constant 1e-3).  ref: pddp/utils/encoding.py:263-301"""
+    D = state_size or infer_state_size(Z.shape[-1], encoding)
+    if encoding == StateEncoding.STANDARD_DEVIATION_ONLY:
+        return Z[..., D:]
+    return decode_var(Z, encoding, D).sqrt()
 
-    def __init__(self, mean, covar=None, var=None, std=None):
-        self._mean, self._covar, self._var, self._std = mean, covar, var, std
 
-    def mean(self):
-        return self._mean
-
-    def encode(self, encoding=StateEncoding.DEFAULT):
-        return encode(self._mean, C=self._covar, V=self._var, S=self._std, encoding=encoding)
+def decode_covar_sqrt(Z, encoding=StateEncoding.DEFAULT, state_size=None):
+    """Upper-triangular U with U^T U = covariance, [..., D, D]: the stored factor for UT-Cholesky, the jittered
+    Cholesky factor of the stored matrix for FULL_COVARIANCE_MATRIX, diagonal for the variance / std encodings,
+    1e-3 I for IGNORE_UNCERTAINTY.  ref: pddp/utils/encoding.py:304-362"""
+    D = state_size or infer_state_size(Z.shape[-1], encoding)
+    other = Z[..., D:]
+    if encoding == StateEncoding.FULL_COVARIANCE_MATRIX:
+        return _jittered_cholesky_upper(other.reshape(*Z.shape[:-1], D, D))
+    if encoding == StateEncoding.UPPER_TRIANGULAR_CHOLESKY:
+        iu = torch.triu_indices(D, D, device=Z.device)
+        U = torch.zeros(*Z.shape[:-1], D, D, dtype=Z.dtype, device=Z.device)
+        U[..., iu[0], iu[1]] = other
+        return U
+    if encoding == StateEncoding.VARIANCE_ONLY:
+        return torch.diag_embed(other.sqrt())
+    if encoding == StateEncoding.STANDARD_DEVIATION_ONLY:
+        return torch.diag_embed(other)
+    return (1e-3 * torch.eye(D, dtype=Z.dtype, device=Z.device)).expand(*Z.shape[:-1], D, D)

@@ -23,7 +23,7 @@ SPEC_FN = {"pendulum": O.pendulum_spec, "cartpole": O.cartpole_spec,
 def all_tags():
     """Per-pass fixtures (known_* / bnn_*); the closed-loop fixtures (loop_*) have their own loader."""
     return sorted(t for t in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not t.startswith("loop_"))
+                  if not t.startswith(("loop_", "train_")))
 
 
 def loop_tags():

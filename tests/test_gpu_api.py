@@ -11,17 +11,17 @@ pytestmark = pytest.mark.gpu
 
 def build(fx):
     import pddp_b200 as P
-    models, costs = P.models, P.costs
+    models, costs, examples = P.models, P.costs, P.examples
     if fx.name == "rendezvous":     # the fixtures use RendezvousCost's Q with a non-degenerate R (oracle/make_golden.py)
-        assert torch.equal(costs.RendezvousCost().Q.data.double(), fx.t("Q").double())
+        assert torch.equal(examples.rendezvous.RendezvousCost().Q.data.double(), fx.t("Q").double())
         cost = costs.QRCost(fx.t("Q"), fx.t("R"), state_size=8, angular_indices=()).to(fx.dtype)
     else:
-        cost = {"pendulum": costs.PendulumCost, "cartpole": costs.CartpoleCost,
-                "double_cartpole": costs.DoubleCartpoleCost}[fx.name]().to(fx.dtype)
+        cost = {"pendulum": examples.pendulum.PendulumCost, "cartpole": examples.cartpole.CartpoleCost,
+                "double_cartpole": examples.double_cartpole.DoubleCartpoleCost}[fx.name]().to(fx.dtype)
     if fx.is_bnn:
         ang = {"cartpole": ([2], [0, 1, 3]), "double_cartpole": ([2, 4], [0, 1, 3, 5])}[fx.name]
         hidden = [int(h) for h in fx.raw["hidden"]]
-        model = models.bnn_dynamics_model_factory(fx.D, 1, hidden, *ang)(n_particles=int(fx.raw["P"])).to(fx.dtype)
+        model = models.bnn.bnn_dynamics_model_factory(fx.D, 1, hidden, *ang)(n_particles=int(fx.raw["P"])).to(fx.dtype)
         with torch.no_grad():
             for name, i in (("fc_0", 0), ("fc_1", 1), ("fc_out", 2)):
                 getattr(model.model, name).weight.copy_(fx.t("W%d" % i))
@@ -39,9 +39,9 @@ def build(fx):
             opts["use_predicted_std"] = True
             opts["independent_noise"] = bool(int(fx.raw["independent_noise"]))
     else:
-        cls = {"pendulum": models.PendulumDynamicsModel, "cartpole": models.CartpoleDynamicsModel,
-               "double_cartpole": models.DoubleCartpoleDynamicsModel,
-               "rendezvous": models.RendezvousDynamicsModel}[fx.name]
+        cls = {"pendulum": examples.pendulum.PendulumDynamicsModel, "cartpole": examples.cartpole.CartpoleDynamicsModel,
+               "double_cartpole": examples.double_cartpole.DoubleCartpoleDynamicsModel,
+               "rendezvous": examples.rendezvous.RendezvousDynamicsModel}[fx.name]
         model = cls(**fx.known_params()).to(fx.dtype)
         opts = {}
     return model, cost, opts

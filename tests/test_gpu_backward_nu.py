@@ -111,12 +111,12 @@ def test_stock_rendezvous_cost_degenerate_quu():
     """RendezvousCost as shipped (R = 0.1 I) makes Q_uu a multiple of the identity: the reference's
     (E/e)E^T with LAPACK's non-orthogonal eigenvectors of a repeated eigenvalue is rounding noise, the
     kernel returns the regularised inverse (oracle with orthonormal eigenvectors).  Whole API path:
-    models.RendezvousDynamicsModel + costs.RendezvousCost -> forward / backward."""
+    examples.rendezvous.RendezvousDynamicsModel + examples.rendezvous.RendezvousCost -> forward / backward."""
     import pddp_b200 as P
     from pddp_b200 import controllers as C
     torch.manual_seed(3)
     N, enc = 9, O.IGNORE_UNCERTAINTY
-    model, cost = P.models.RendezvousDynamicsModel(0.1).double(), P.costs.RendezvousCost().double()
+    model, cost = P.examples.rendezvous.RendezvousDynamicsModel(0.1).double(), P.examples.rendezvous.RendezvousCost().double()
     z0 = torch.tensor([-10.0, -10.0, 10.0, 10.0, 0.0, -5.0, 5.0, 0.0], dtype=torch.float64)
     U = 0.1 * torch.randn(N, 4, dtype=torch.float64)
     lin = C.forward(z0.cuda(), U.cuda(), model, cost, enc)

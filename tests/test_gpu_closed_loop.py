@@ -16,15 +16,15 @@ def build(name, fx):
     import pddp_b200 as P
     torch.set_default_dtype(torch.float64)
     try:
-        model = {"pendulum": P.models.PendulumDynamicsModel, "cartpole": P.models.CartpoleDynamicsModel,
-                 "rendezvous": P.models.RendezvousDynamicsModel}[name](0.1)
+        model = {"pendulum": P.examples.pendulum.PendulumDynamicsModel, "cartpole": P.examples.cartpole.CartpoleDynamicsModel,
+                 "rendezvous": P.examples.rendezvous.RendezvousDynamicsModel}[name](0.1)
         if name == "rendezvous":
             cost = P.costs.QRCost(fx["Q"], fx["R"], state_size=8, angular_indices=())
         else:
-            cost = {"pendulum": P.costs.PendulumCost, "cartpole": P.costs.CartpoleCost}[name]()
+            cost = {"pendulum": P.examples.pendulum.PendulumCost, "cartpole": P.examples.cartpole.CartpoleCost}[name]()
         cost = cost.double()
-        env_cls = {"pendulum": P.envs.PendulumEnv, "cartpole": P.envs.CartpoleEnv,
-                   "rendezvous": P.envs.RendezvousEnv}[name]
+        env_cls = {"pendulum": P.examples.pendulum.PendulumEnv, "cartpole": P.examples.cartpole.CartpoleEnv,
+                   "rendezvous": P.examples.rendezvous.RendezvousEnv}[name]
     finally:
         torch.set_default_dtype(torch.float32)
     return model, cost, env_cls
@@ -35,8 +35,8 @@ def build(name, fx):
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_env_step_matches_the_oracle_model(name, kind, dtype):
     import pddp_b200 as P
-    env_cls = {"pendulum": P.envs.PendulumEnv, "cartpole": P.envs.CartpoleEnv,
-               "double_cartpole": P.envs.DoubleCartpoleEnv, "rendezvous": P.envs.RendezvousEnv}[name]
+    env_cls = {"pendulum": P.examples.pendulum.PendulumEnv, "cartpole": P.examples.cartpole.CartpoleEnv,
+               "double_cartpole": P.examples.double_cartpole.DoubleCartpoleEnv, "rendezvous": P.examples.rendezvous.RendezvousEnv}[name]
     B = 300
     env = env_cls(dt=0.1, batch_size=B, dtype=dtype, generator=torch.Generator().manual_seed(1))
     assert env.state_size == env.get_state().mean().shape[-1] and env.get_state().mean().shape[0] == B

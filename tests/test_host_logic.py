@@ -11,7 +11,8 @@ import torch
 
 import pddp_oracle as O
 import pddp_b200
-from pddp_b200 import _lib, controllers, costs, encoding, models
+from pddp_b200 import _lib, controllers, costs, examples, models
+from pddp_b200.utils import encoding
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -36,8 +37,8 @@ def test_struct_layouts():
 
 
 def test_no_cpu_fallback():
-    cost = costs.PendulumCost()
-    model = models.PendulumDynamicsModel(0.1)
+    cost = examples.pendulum.PendulumCost()
+    model = examples.pendulum.PendulumDynamicsModel(0.1)
     with pytest.raises(RuntimeError, match="CUDA"):
         controllers.forward(torch.zeros(2), torch.zeros(5, 1), model, cost, encoding.StateEncoding.IGNORE_UNCERTAINTY)
     with pytest.raises(RuntimeError, match="CUDA"):
@@ -70,23 +71,23 @@ def test_unsupported_configurations_raise():
         models.geometry_of(5, (1,))                    # no kernels for an arbitrary geometry
     assert models.geometry_of(8, ()) == _lib.GEO_RENDEZVOUS
     with pytest.raises(NotImplementedError):
-        models.bnn_dynamics_model_factory(4, 2, [200, 200], [2], [0, 1, 3])
-    Model = models.bnn_dynamics_model_factory(4, 1, [32, 32], [2], [0, 1, 3])
+        models.bnn.bnn_dynamics_model_factory(4, 2, [200, 200], [2], [0, 1, 3])
+    Model = models.bnn.bnn_dynamics_model_factory(4, 1, [32, 32], [2], [0, 1, 3])
     with pytest.raises(NotImplementedError):
-        controllers.iLQRController(None, Model(n_particles=8), costs.CartpoleCost(),
+        controllers.iLQRController(None, Model(n_particles=8), examples.cartpole.CartpoleCost(),
                                    model_opts={"resample": True})
     with pytest.raises(NotImplementedError):
         controllers.backward(*[torch.zeros(1)] * 9, V_zz_reg=True)
 
 
 def test_cost_constants_match_reference_examples():
-    c = costs.CartpoleCost()
+    c = examples.cartpole.CartpoleCost()
     assert c.Q[0, 3] == 0.5 and c.Q[3, 3] == 0.25 and c.Q_term.equal(torch.eye(5))
     assert torch.allclose(c.x_goal, torch.tensor([0, 0, 0, -8.742278e-08, -1.0]))   # fp32 sin(pi), cos(pi)
-    d = costs.DoubleCartpoleCost()
+    d = examples.double_cartpole.DoubleCartpoleCost()
     assert torch.allclose(d.Q[0, 4:], torch.tensor([-0.6, 0.0, -0.6, 0.0]))
     assert d.Q_term.equal(100 * torch.eye(8)) and d.x_goal.tolist() == [0, 0, 0, 0, 0, 1, 0, 1]
-    p = costs.PendulumCost()
+    p = examples.pendulum.PendulumCost()
     assert p.Q[0, 1] == 0.5 and p.R[0, 0] == pytest.approx(0.1)
 
 
@@ -123,7 +124,7 @@ def test_q_function_matches_oracle():
 
 
 def test_bnn_model_draws_reference_style_state():
-    Model = models.bnn_dynamics_model_factory(4, 1, [200, 200], [2], [0, 1, 3])
+    Model = models.bnn.bnn_dynamics_model_factory(4, 1, [200, 200], [2], [0, 1, 3])
     m = Model(n_particles=50)
     m.resample(torch.Generator().manual_seed(0))
     d = m.descriptor()
@@ -139,7 +140,7 @@ def test_bnn_model_options_map_to_the_descriptor():
     """infer_noise_variables / sample_input_distribution / use_predicted_std / independent_noise
     (ref: pddp/models/bnn/modules.py:242-262, 320-358) -> BNNDynamics.input_mode / eps_in / eps_out;
     noise the reference would draw lazily is drawn per step, standardised, and then kept."""
-    Model = models.bnn_dynamics_model_factory(4, 1, [32, 32], [2], [0, 1, 3])
+    Model = models.bnn.bnn_dynamics_model_factory(4, 1, [32, 32], [2], [0, 1, 3])
     m = Model(n_particles=9)
     m.resample(torch.Generator().manual_seed(0))
     d = m.descriptor({}, 6)
@@ -166,17 +167,16 @@ def test_bnn_model_options_map_to_the_descriptor():
 
 def test_rendezvous_and_envs_host_side():
     """action_size 4 constants reach the C structs; environments refuse to live on the CPU."""
-    from pddp_b200 import envs
-    c = costs.RendezvousCost()
+    c = examples.rendezvous.RendezvousCost()
     assert c.Q[0, 2] == -1 and c.Q[3, 1] == -1 and c.R.shape == (4, 4) and c.Q_term.equal(c.Q)
     s = c.constants().c_struct()
     assert [s.R[i] for i in (0, 1, 5, 15)] == pytest.approx([0.1, 0.0, 0.1, 0.1])
     assert list(s.u_goal) == [0.0] * 4
-    m = models.RendezvousDynamicsModel(0.1)
+    m = examples.rendezvous.RendezvousDynamicsModel(0.1)
     assert (m.state_size, m.action_size) == (8, 4) and m.descriptor().geo == _lib.GEO_RENDEZVOUS
     assert m.descriptor().params == pytest.approx([0.1, 1.0, 0.1])
     with pytest.raises(RuntimeError, match="CUDA"):
-        envs.PendulumEnv(dt=0.1, device="cpu")
+        examples.pendulum.PendulumEnv(dt=0.1, device="cpu")
     names = list(inspect.signature(controllers._apply_controller).parameters)
     assert names[:8] == ["env", "cost", "controller", "H", "encoding", "mpc", "quiet", "cost_opts"]   # ref: pddp.py:209-217
-    assert pddp_b200.examples.rendezvous.RendezvousEnv is envs.RendezvousEnv
+    assert issubclass(examples.rendezvous.RendezvousEnv, pddp_b200.envs.KnownDynamicsEnv)

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pddp_b200.sharding import gather_to_rank0, shard, shard_bounds
+from pddp_b200.sharding import all_gather_problems, gather_to_rank0, shard, shard_bounds, world_and_rank
 
 
 def _worker(rank, world, port, B, out_path):
@@ -22,6 +22,13 @@ def _worker(rank, world, port, B, out_path):
         torch.save(got, out_path)
     else:
         assert got is None
+    # the product's final exchange (iLQRController.fit under torchrun): Z, U, K, state in ONE all-gather
+    assert world_and_rank() == (world, rank)
+    Z = mine.double() + 0.5
+    state = torch.arange(lo, hi, dtype=torch.int32)
+    fZ, fU, fs = all_gather_problems([Z, result, state], B)
+    assert torch.equal(fZ, full.double() + 0.5) and torch.equal(fU, full * 2 + 1)
+    assert torch.equal(fs, torch.arange(B, dtype=torch.int32))
     dist.destroy_process_group()
 
 

@@ -13,11 +13,18 @@ states": UT-Cholesky encoding (nz=14), MLP 6->200->200->8, 10 line-search alphas
 Synthetic data: random-init BNN weights (reference initialiser, fc_out x0.02 so 100-step rollouts
 stay finite -- SURVEY.md 6), CDropout eval masks and standardised eps_in[0] drawn once.
 
+The JSON line also carries (rank 0): `roofline` (dominant kernel + per-kernel HBM / tensor fractions from CUDA
+events on the launch stream), `e2e` (the same metric through `iLQRController.fit` with HOST buffers),
+`cpu_baseline` (the CPU port of the reference on this box's host cores), `other_workloads` (BASELINE configs
+1, 3, 4, 5 and config 2 in fp64, a few steps each) and, for N > 1, `strong` (config 2's 4096 problems split over
+the ranks) and the timed final NCCL all-gather.
+
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU, no collective in
                                                                  the iteration, final NCCL gather)
 """
 import argparse
+import ctypes as C
 import json
 import math
 import os
@@ -38,14 +45,21 @@ WORKLOADS = {
                                               hidden=200, umax=20.0),
     "cartpole_bnn_mpc_b8192": dict(problem="cartpole", enc=1, B=8192, N=50, P=50, A=16, hidden=200, umax=10.0),
     "pendulum_known_b1m": dict(problem="pendulum", enc=4, B=1 << 20, N=100, P=0, A=10, hidden=0, umax=2.5),
+    # BASELINE configs[0]: one pendulum problem (launch-latency bound on any GPU; reported for completeness)
+    "pendulum_known_single": dict(problem="pendulum", enc=4, B=1, N=100, P=0, A=10, hidden=0, umax=2.5),
     "cartpole_bnn_small": dict(problem="cartpole", enc=1, B=64, N=10, P=50, A=10, hidden=200, umax=10.0),
     # action_size 4 (Jacobi eigen-clipping + 4-dimensional box QP in the backward pass)
     "rendezvous_known_b64k": dict(problem="rendezvous", enc=4, B=1 << 16, N=100, P=0, A=10, hidden=0, umax=1.0),
 }
+OTHER_WORKLOADS = (("pendulum_known_single", "f32"), ("double_cartpole_bnn_fullcov_b1024", "f32"),
+                   ("pendulum_known_b1m", "f32"), ("cartpole_bnn_mpc_b8192", "f32"), ("cartpole_bnn_b4096", "f64"),
+                   ("pendulum_known_b1m", "f64"), ("rendezvous_known_b64k", "f32"))
 GEOMETRY = {"pendulum": (0, 2, (0,), (1,)), "cartpole": (1, 4, (2,), (0, 1, 3)),
             "double_cartpole": (2, 6, (2, 4), (0, 1, 3, 5)), "rendezvous": (3, 8, (), tuple(range(8)))}
 KNOWN_PARAMS = {"pendulum": [0.1, 1.0, 1.0, 0.1, 9.80665], "rendezvous": [0.1, 1.0, 0.1]}
 ACTION_SIZE = {"rendezvous": 4}
+PROFILE_KINDS = ("mlp_linearise", "mlp_rollout", "moment_linearise", "rollout_step", "backward", "cost",
+                 "linearize_known", "rollout_known", "accept")
 
 
 def cost_constants(problem, dtype=torch.float64):
@@ -65,10 +79,10 @@ def cost_constants(problem, dtype=torch.float64):
         Q = torch.eye(8, dtype=dtype)
         Q[0, 2] = Q[2, 0] = Q[1, 3] = Q[3, 1] = -1
         return Q, 0.1 * torch.eye(4, dtype=dtype), Q.clone(), torch.zeros(8, dtype=dtype)
-    C = torch.tensor([[1, -.6, 0, -.6, 0], [0, 0, .6, 0, .6]], dtype=dtype)
+    C_ = torch.tensor([[1, -.6, 0, -.6, 0], [0, 0, .6, 0, .6]], dtype=dtype)
     Q = torch.zeros(8, 8, dtype=dtype)
     dims = [0, 4, 5, 6, 7]
-    Q[torch.tensor(dims)[:, None], torch.tensor(dims)[None, :]] = C.T @ C
+    Q[torch.tensor(dims)[:, None], torch.tensor(dims)[None, :]] = C_.T @ C_
     goal = torch.tensor([0, 0, 0, 0, 0, 1, 0, 1.0], dtype=dtype)
     return Q, 0.1 * torch.eye(1, dtype=dtype), 100 * torch.eye(8, dtype=dtype), goal
 
@@ -170,6 +184,21 @@ def measured_peaks():
     return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
+def committed_traffic(workload, kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel from the committed
+    `ncu --set full` export profiles/kernel_traffic.json (written by tools/ncu_summary.py --traffic); None when
+    the kernel has no committed capture."""
+    path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        table = json.load(f)
+    row = table.get(workload, {}).get(kernel)
+    if not row:
+        return None, None
+    return float(row["dram_bytes_per_launch"]), row.get("source")
+
+
 # ---------------------------------------------------------------------------------------------
 def oracle_problem(w, dtype, n_problems, seed):
     """The same synthetic workload expressed for the CPU oracle (checker / cpu baseline only)."""
@@ -187,23 +216,50 @@ def oracle_problem(w, dtype, n_problems, seed):
     return O, dyn, cost, z0, U
 
 
-def time_oracle(w, dtype, n_problems, seed=0):
-    """Seconds for `n_problems` sequential problem-iterations of the reference algorithm on the
-    host cores (the reference optimises one problem at a time, SURVEY.md section 2 note)."""
-    O, dyn, cost, z0, U = oracle_problem(w, dtype, n_problems, seed)
+def oracle_iteration(O, dyn, cost, z0, U, w, dtype):
+    """One problem-iteration of the reference algorithm: linearise, backward, rollout of every alpha, cost, argmin
+    (pddp/controllers/ilqr.py:183-235 with mu = 1, as in the GPU step)."""
     nu = ACTION_SIZE.get(w["problem"], 1)
     lo, hi = torch.full((nu,), -w["umax"], dtype=dtype), torch.full((nu,), w["umax"], dtype=dtype)
     alphas = O.fit_alphas(dtype, w["A"])
-    t0 = time.perf_counter()
-    for i in range(n_problems):
-        lin = O.linearize(z0[i], U[i], dyn, cost, w["enc"], lo, hi)
-        try:
-            k, K = O.backward_pass(*lin, reg=1.0, u_min=lo, u_max=hi, U=U[i])
-            Zb, Ub = O.rollout(dyn, lin[0], U[i], k, K, alphas, w["enc"], lo, hi)
-            O.trajectory_cost(cost, Zb, Ub, w["enc"]).argmin()
-        except RuntimeError:
-            pass
-    return time.perf_counter() - t0
+    lin = O.linearize(z0, U, dyn, cost, w["enc"], lo, hi)
+    try:
+        k, K = O.backward_pass(*lin, reg=1.0, u_min=lo, u_max=hi, U=U)
+        Zb, Ub = O.rollout(dyn, lin[0], U, k, K, alphas, w["enc"], lo, hi)
+        O.trajectory_cost(cost, Zb, Ub, w["enc"]).argmin()
+    except RuntimeError:
+        pass
+
+
+def time_oracle(w, dtype, n_problems, passes, budget_s, seed=0):
+    """Warm-up, then `passes` timed sweeps over `n_problems` problems, sequentially (the reference optimises one
+    problem at a time, SURVEY.md section 2 note).  Stops early once the budget is spent and at least 3
+    problem-iterations are timed.  Returns the list of seconds per problem-iteration."""
+    O, dyn, cost, z0, U = oracle_problem(w, dtype, n_problems, seed)
+    warm = dict(w, N=min(w["N"], 5))
+    oracle_iteration(O, dyn, cost, z0[0], U[0, :warm["N"]], warm, dtype)          # warm-up (autograd / thread pools)
+    times, t_start = [], time.perf_counter()
+    for _ in range(passes):
+        for i in range(n_problems):
+            t0 = time.perf_counter()
+            oracle_iteration(O, dyn, cost, z0[i], U[i], w, dtype)
+            times.append(time.perf_counter() - t0)
+            if len(times) >= 3 and time.perf_counter() - t_start > budget_s:
+                return times
+    return times
+
+
+def cpu_baseline_record(w, budget_s=30.0):
+    """warm-up + >= 3 timed problem-iterations over min(B, 8) problems, all host cores."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = min(w["B"], 8)
+    times = time_oracle(w, torch.float32, n, passes=3, budget_s=budget_s)
+    mean = sum(times) / len(times)
+    return {"value": w["N"] / mean, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
+            "sample": "warm-up + %d timed problem-iterations over %d problem(s) of the same workload, %.2f s each "
+                      "(min %.2f, max %.2f); the reference handles one problem at a time, so the batch figure is "
+                      "extrapolated from these" % (len(times), min(n, len(times)), mean, min(times), max(times))}
 
 
 def run_reference(args, w, rank):
@@ -214,79 +270,94 @@ def run_reference(args, w, rank):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     dtype = torch.float32
-    sample = 1
-    for _ in range(args.warmup and 1):
-        time_oracle(dict(w, N=min(w["N"], 5)), dtype, 1)
-    times = [time_oracle(w, dtype, sample, seed=i) for i in range(args.steps)]
-    sec = sum(times)
-    value = sample * w["N"] * args.steps / sec
+    O, dyn, cost, z0, U = oracle_problem(w, dtype, min(w["B"], 8), 0)
+    warm = dict(w, N=min(w["N"], 5))
+    for _ in range(max(1, min(args.warmup, 2))):
+        oracle_iteration(O, dyn, cost, z0[0], U[0, :warm["N"]], warm, dtype)
+    t0 = time.perf_counter()
+    for i in range(args.steps):                      # one step = one problem-iteration (problems cycle)
+        oracle_iteration(O, dyn, cost, z0[i % z0.shape[0]], U[i % z0.shape[0]], w, dtype)
+    sec = time.perf_counter() - t0
+    value = w["N"] * args.steps / sec
     line = {"impl": "reference", "metric": "trajectory-steps/s", "value": value, "unit": "trajectory-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.workload, w),
             "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
-                             "sample": "%d problem(s) x 1 iteration per step (the reference handles one problem "
-                                       "at a time; whole-batch time = B x this)" % sample},
+                             "sample": "1 problem x 1 iteration per step over %d distinct problems (the reference "
+                                       "handles one problem at a time; whole-batch time = B x this)" % min(w["B"], 8)},
             "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def enc_size(w):
+    D = GEOMETRY[w["problem"]][1]
+    return {4: D, 1: (3 * D + D * D) // 2, 0: D * (1 + D)}[w["enc"]]
+
+
 def workload_config(name, w):
-    nz = {4: GEOMETRY[w["problem"]][1], 1: (3 * GEOMETRY[w["problem"]][1] + GEOMETRY[w["problem"]][1] ** 2) // 2,
-          0: GEOMETRY[w["problem"]][1] * (1 + GEOMETRY[w["problem"]][1])}[w["enc"]]
     return {"workload": name, "problems_per_gpu": w["B"], "horizon": w["N"], "particles": w["P"],
-            "alphas": w["A"], "nz": nz, "hidden": [w["hidden"]] * 2 if w["hidden"] else None,
+            "alphas": w["A"], "nz": enc_size(w), "hidden": [w["hidden"]] * 2 if w["hidden"] else None,
             "encoding": {0: "FULL_COVARIANCE_MATRIX", 1: "UPPER_TRIANGULAR_CHOLESKY", 4: "IGNORE_UNCERTAINTY"}[w["enc"]],
-            "bounded": True, "mu": 1.0, "l2": "inputs_exceed_l2 (per-step working set >> 126 MB)",
+            "bounded": True, "mu": 1.0, "l2": "inputs_exceed_l2 (per-step working set >> 126 MB)" if w["B"] > 64 else
+            "working set fits L2 (single problem; launch-latency bound)",
             "parallelism": "independent problems sharded per GPU, no collective in the iteration"}
 
 
 # ---------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cartpole_bnn_b4096", choices=sorted(WORKLOADS))
-    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    w = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, w, rank)
-        return
-    if args.warmup < 3:
-        args.warmup = 3
+# Algorithmic work per trajectory-step: elements moved through HBM by each stage, MLP flops
+# ---------------------------------------------------------------------------------------------
+def stage_elements(nz, nu):
+    E_lw = 2 * nz * nz + 2 * nz * nu + 2 * nz + nu + nu * nu + 1          # linearise writes Z,F_z,F_u,L,L_z,L_u,L_zz,L_uz,L_uu
+    E_br = 2 * nz * nz + 2 * nz * nu + nz + nu + nu * nu                  # backward reads
+    cost_w = 1 + nz + nu + nz * nz + nu * nz + nu * nu
+    return {
+        "linearize_known": E_lw + nu,
+        "moment_linearise": nz * nz + nz * nu + nz,                       # F_z, F_u, Z[t+1] written by the BNN linearise step
+        "cost": cost_w + nz + nu,
+        "backward": E_br + nu + nu * nz,
+        "rollout_known": (nz + 2 * nu + nu * nz) + (nz + nu),
+        "rollout_step": (nz + 2 * nu + nu * nz) + (nz + nu),
+        "accept": 2 * (nz + nu) + 2 * nu * nz,
+        "whole_pass": (E_lw + nu) + (E_br + nu + nu * nz) + (nz + 2 * nu + nu * nz) + (nz + nu),
+    }
 
-    import torch.distributed as dist
-    from pddp_b200 import _lib
+
+def mlp_tile_flops(w):
+    """Tensor FLOPs the tcgen05 kernel EXECUTES per 128-row tile (bnn_mlp_tc.cuh): layer 1 = 3 split-FP16 passes of
+    M128 x N208 x K16 per 16-wide K-block of the (H0 + 1)-wide hidden vector (the +1 is the bias unit), layer 0 = 2
+    MMAs of M128 x N32 x K16 per 32-unit chunk.  Compare with the algorithmic 2 * MACs per row."""
+    H = w["hidden"]
+    nkb = (H + 1 + 15) // 16
+    chunks = (H + 1 + 31) // 32
+    return 2.0 * 128 * (3 * nkb * 208 * 16 + 2 * chunks * 32 * 16)
+
+
+def build_solver(name, dtype, dev, rank, B=None):
     from pddp_b200.solver import BatchedSolver, BNNDynamics, KnownDynamics, QRCostConstants
-
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    dtype = torch.float32 if args.dtype == "f32" else torch.float64
-    lib = _lib.load()
+    w = dict(WORKLOADS[name])
+    if B is not None:
+        w["B"] = B
     geo, D, ang, nonang = GEOMETRY[w["problem"]]
-    Q, R, Qt, goal = cost_constants(w["problem"])
-    cost = QRCostConstants(Q, R, Qt, goal)
+    cost = QRCostConstants(*cost_constants(w["problem"]))
     if w["P"]:
-        W, b, masks, eps0 = synth_bnn(w["problem"], w["P"], w["hidden"], seed=0)
-        dyn = BNNDynamics(geo, W, b, masks, eps0)
+        dyn = BNNDynamics(geo, *synth_bnn(w["problem"], w["P"], w["hidden"], seed=0))
     else:
         dyn = KnownDynamics(geo, KNOWN_PARAMS[w["problem"]])
     solver = BatchedSolver(dyn, cost, w["enc"], w["B"], w["N"], dtype=dtype, device=dev, max_alphas=w["A"])
     z0_h, U_h = synth_inputs(w, seed=1 + rank, dtype=dtype)
-    z0_h, U_h = z0_h.pin_memory(), U_h.pin_memory()
     nu = ACTION_SIZE.get(w["problem"], 1)
     lo, hi = [-w["umax"]] * nu, [w["umax"]] * nu
     alphas = (1.025 ** (-torch.arange(float(w["A"]), dtype=torch.float64) ** 2)).to(dtype)
     solver.set_problem(z0_h.to(dev), U_h.to(dev), lo, hi, alphas=alphas, iterations=1 << 30)
+    return w, solver, z0_h, U_h, lo, hi, alphas
+
+
+def measure(name, dtype, steps, warmup, dev, rank, world, dist, B=None, profile=True):
+    """Device-timed passes of one workload + per-kernel times from CUDA events on the launch stream."""
+    from pddp_b200 import _lib
+    lib = _lib.load()
+    w, solver, z0_h, U_h, lo, hi, alphas = build_solver(name, dtype, dev, rank, B)
 
     def step():
         # every problem stays in play with a fixed regularisation so the work per step is constant
@@ -300,15 +371,15 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     sync_all()
     not_pd = int((solver.bw_status != 0).sum().item())
     launches0 = int(lib.pddp_launch_count())
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(dev.index) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     sync_all()
@@ -319,114 +390,241 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     not_pd = max(not_pd, int((solver.bw_status != 0).sum().item()))
-    total_steps = world * w["B"] * w["N"] * args.steps
-    value = total_steps / (ms * 1e-3)
+    rec = {"w": w, "solver": solver, "ms_per_step": ms / steps, "value": world * w["B"] * w["N"] * steps / (ms * 1e-3),
+           "launches": launches, "clocks": clocks, "not_pd": not_pd, "step": step, "sync_all": sync_all,
+           "host": (z0_h, U_h, lo, hi, alphas), "kernels": None}
+    if profile:
+        n = len(PROFILE_KINDS)
+        lib.pddp_profile_enable(1)
+        step()
+        pms, pcnt = (C.c_double * n)(), (C.c_int64 * n)()
+        _lib.check(lib.pddp_profile_read(pms, pcnt), "profile_read")
+        lib.pddp_profile_enable(0)
+        rec["kernels"] = {k: (pms[i], int(pcnt[i])) for i, k in enumerate(PROFILE_KINDS) if pcnt[i]}
+    return rec
 
-    # ---- end to end: host buffers in, host buffers out, every step ------------------------------
-    Z_h = torch.empty(solver.view("Z").shape, dtype=dtype).pin_memory()
-    Uo_h = torch.empty(solver.view("U").shape, dtype=dtype).pin_memory()
-    J_h = torch.empty(w["B"], dtype=dtype).pin_memory()
+
+def roofline_record(name, rec, dtype, peaks):
+    """`roofline` of a workload: the dominant kernel against its bound, plus every profiled kernel with its own
+    fraction (HBM kernels: algorithmic bytes / event time / measured copy bandwidth; MLP: algorithmic and executed
+    tensor FLOP/s against the measured sustained bf16 rate)."""
+    hbm_peak, tensor_peak, peak_src = peaks
+    w, solver = rec["w"], rec["solver"]
+    s = 4 if dtype == torch.float32 else 8
+    nz, nu, BN = solver.nz, solver.nu, w["B"] * w["N"]
+    elems = stage_elements(nz, nu)
+    ms_step = rec["ms_per_step"]
+    kernels = {}
+    tc_path = bool(w["P"]) and dtype == torch.float32 and 64 < w["hidden"] <= 207
+    rows = {}
+    if w["P"]:
+        geo, D, ang, _ = GEOMETRY[w["problem"]]
+        macs = sum(a * b_ for a, b_ in zip([D + len(ang) + 1, w["hidden"], w["hidden"]], [w["hidden"], w["hidden"], 2 * D]))
+        rows = {"mlp_linearise": w["B"] * w["P"] * (1 + D + 1), "mlp_rollout": w["B"] * w["A"] * w["P"]}
+    for kind, (ms, cnt) in (rec["kernels"] or {}).items():
+        k = {"launches_per_step": cnt, "avg_ms": ms / cnt, "ms_per_step": ms, "share_of_step": ms / ms_step}
+        if kind in rows:
+            flops = 2.0 * macs * rows[kind]                       # per launch (one time step of the whole batch)
+            k.update(bound="tensor", algorithmic_flops_per_launch=flops,
+                     achieved_tflops=flops / (ms / cnt * 1e-3) / 1e12,
+                     frac=flops / (ms / cnt * 1e-3) / 1e12 / tensor_peak)
+            if tc_path:
+                tiles = w["P"] * math.ceil(rows[kind] / w["P"] / 128)
+                ex = tiles * mlp_tile_flops(w)
+                k.update(executed_tflops=ex / (ms / cnt * 1e-3) / 1e12, executed_per_algorithmic=ex / flops,
+                         executed_frac_of_peak=ex / (ms / cnt * 1e-3) / 1e12 / tensor_peak)
+        elif kind in elems:
+            nbytes = elems[kind] * s * BN                         # per step (all launches of the kind together)
+            k.update(bound="hbm", algorithmic_bytes_per_step=nbytes, achieved_gbs=nbytes / (ms * 1e-3) / 1e9,
+                     frac=nbytes / (ms * 1e-3) / 1e9 / hbm_peak)
+        kernels[kind] = k
+    if w["P"] and kernels:
+        dom = max(("mlp_linearise", "mlp_rollout"), key=lambda k_: kernels.get(k_, {}).get("ms_per_step", 0.0))
+        d = kernels[dom]
+        traffic, tsrc = committed_traffic(name, dom)
+        return {"bound": "tensor", "kernel": "bnn_mlp (%s rows)" % dom.split("_")[1], "achieved": d["achieved_tflops"],
+                "peak": tensor_peak, "unit": "TFLOP/s", "frac": d["frac"], "traffic": traffic, "traffic_source": tsrc,
+                "peak_source": "bf16 dense sustained, " + peak_src,
+                "executed_tflops": d.get("executed_tflops"), "executed_per_algorithmic": d.get("executed_per_algorithmic"),
+                "tensor_passes_per_product": 3 if tc_path else None,
+                "note": "achieved = ALGORITHMIC flops (2 x MACs per row) / mean launch time; executed_tflops = tensor "
+                        "FLOPs the kernel issues (3 split-FP16 passes per fp32-accurate product + tile padding)",
+                "flops_per_launch": d["algorithmic_flops_per_launch"], "avg_launch_ms": d["avg_ms"],
+                "mlp_share_of_step": sum(kernels[k_]["ms_per_step"] for k_ in rows if k_ in kernels) / ms_step,
+                "kernels": kernels}
+    nbytes = elems["whole_pass"] * s * BN
+    achieved = nbytes / (ms_step * 1e-3) / 1e9
+    dom = max(kernels, key=lambda k_: kernels[k_]["ms_per_step"]) if kernels else None
+    traffic, tsrc = committed_traffic(name, dom) if dom else (None, None)
+    return {"bound": "hbm", "kernel": "whole pass (linearise+backward+rollout+accept); slowest kernel: %s" % dom,
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+            "traffic_source": tsrc, "peak_source": "copy bandwidth, " + peak_src, "kernels": kernels}
+
+
+def controller_for(name, w, dtype):
+    """The synthetic workload as the objects a user of the reference API holds (model, cost, controller)."""
+    import pddp_b200 as P
+    from pddp_b200.costs import QRCost
+    geo, D, ang, nonang = GEOMETRY[w["problem"]]
+    Q, R, Qt, goal = cost_constants(w["problem"], dtype)
+    cost = QRCost(Q, R, Qt, goal, state_size=D, angular_indices=ang)
+    if w["P"]:
+        W, b, masks, eps0 = synth_bnn(w["problem"], w["P"], w["hidden"], seed=0)
+        model = P.models.bnn.bnn_dynamics_model_factory(D, 1, [w["hidden"]] * 2, list(ang), list(nonang))(
+            n_particles=w["P"]).to(dtype)
+        model._store_flat(torch.cat([t.reshape(-1) for pair in zip(W, b) for t in pair] + [torch.zeros(2)]).to(dtype))
+        model.model.drop_0.mask, model.model.drop_1.mask = masks[0].to(dtype), masks[1].to(dtype)
+        model.eps_in = {0: eps0.to(dtype)}
+        opts = {"use_predicted_std": False, "infer_noise_variables": True}
+    else:
+        cls = {"pendulum": P.examples.pendulum.PendulumDynamicsModel,
+               "rendezvous": P.examples.rendezvous.RendezvousDynamicsModel}[w["problem"]]
+        model, opts = cls(*KNOWN_PARAMS[w["problem"]]).to(dtype), {}
+    return P.controllers.iLQRController(None, model, cost, model_opts=opts)
+
+
+def measure_e2e(name, rec, dtype, steps, dev, world, dist):
+    """The same metric through the public API -- `iLQRController.fit(U, z0=..., n_iterations=1, max_passes=1)` --
+    with HOST buffers: every step copies z0 / U from pinned host memory and reads Z, U, state (and J) back."""
+    w = rec["w"]
+    z0_h, U_h, lo, hi, _ = rec["host"]
+    z0_h, U_h = z0_h.pin_memory(), U_h.pin_memory()
+    ctrl = controller_for(name, w, dtype)
+    nz, nu = enc_size(w), ACTION_SIZE.get(w["problem"], 1)
+    Z_h = torch.empty(w["B"], w["N"] + 1, nz, dtype=dtype).pin_memory()
+    Uo_h = torch.empty(w["B"], w["N"], nu, dtype=dtype).pin_memory()
     st_h = torch.empty(w["B"], dtype=torch.int32).pin_memory()
+    lo_d, hi_d = torch.tensor(lo, dtype=dtype, device=dev), torch.tensor(hi, dtype=dtype, device=dev)
     h2d = z0_h.numel() * z0_h.element_size() + U_h.numel() * U_h.element_size()
-    d2h = sum(t.numel() * t.element_size() for t in (Z_h, Uo_h, J_h, st_h))
+    d2h = sum(t.numel() * t.element_size() for t in (Z_h, Uo_h, st_h))
 
     def e2e_step():
-        solver.set_problem(z0_h.to(dev, non_blocking=True), U_h.to(dev, non_blocking=True), lo, hi,
-                           alphas=None, iterations=1)
-        solver.mu.fill_(1.0)
-        solver.iterate()
-        Z_h.copy_(solver.view("Z"), non_blocking=True)
-        Uo_h.copy_(solver.view("U"), non_blocking=True)
-        J_h.copy_(solver.J_opt, non_blocking=True)
-        st_h.copy_(solver.state, non_blocking=True)
+        Z, U, state = ctrl.fit(U_h.to(dev, non_blocking=True), encoding=w["enc"], n_iterations=1, max_passes=1,
+                               u_min=lo_d, u_max=hi_d, z0=z0_h.to(dev, non_blocking=True), shard=False, quiet=True)
+        Z_h.copy_(Z, non_blocking=True)
+        Uo_h.copy_(U, non_blocking=True)
+        st_h.copy_(state, non_blocking=True)
         torch.cuda.synchronize(dev)
 
     e2e_step()
-    sync_all()
+    e2e_step()
+    rec["sync_all"]()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
     e1.record()
-    sync_all()
-    ms_e2e = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], device=dev,
-                          dtype=torch.float64)
+    rec["sync_all"]()
+    ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = total_steps / (float(ms_e2e.item()) * 1e-3)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    states = torch.bincount(st_h.long(), minlength=6).tolist()
+    return {"value": world * w["B"] * w["N"] * steps / (float(ms.item()) * 1e-3), "unit": "trajectory-steps/s",
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "api": "iLQRController.fit(U[B,N,nu], z0=[B,nz], n_iterations=1, max_passes=1) from pinned host buffers",
+            "states_after_one_pass": dict(zip(("undefined", "accepted", "rejected", "not_pd", "max_reg", "converged"), states))}
 
-    # ---- dominant kernel: per-launch duration from CUDA events on the launch stream ---------------
-    roofline = None
-    hbm_peak, tensor_peak, peak_src = measured_peaks()
-    if w["P"]:
-        lib.pddp_profile_enable(1)
-        step()
-        import ctypes as C
-        pms, pcnt = (C.c_double * 4)(), (C.c_int64 * 4)()
-        _lib.check(lib.pddp_profile_read(pms, pcnt), "profile_read")
-        lib.pddp_profile_enable(0)
-        macs_per_row = sum(a * b_ for a, b_ in zip([D + len(ang) + 1, w["hidden"], w["hidden"]],
-                                                  [w["hidden"], w["hidden"], 2 * D]))
-        rows = {0: w["B"] * w["P"] * (1 + D + 1), 1: w["B"] * w["A"] * w["P"]}
-        kinds = {}
-        for kind, name in ((0, "mlp_linearise"), (1, "mlp_rollout"), (2, "moment_linearise"), (3, "rollout_step")):
-            if pcnt[kind]:
-                kinds[name] = {"launches_per_step": int(pcnt[kind]), "avg_ms": pms[kind] / pcnt[kind],
-                               "ms_per_step": pms[kind]}
-        dom = 1 if pms[1] >= pms[0] else 0
-        flops = 2.0 * macs_per_row * rows[dom]
-        achieved = flops / (pms[dom] / pcnt[dom] * 1e-3) / 1e12
-        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-        # (profiles/r1_summary.md, default workload only; null for the others)
-        traffic = {1: 36.7e6 + 3.0e6, 0: 4.6e6 + 0.2e6}[dom] if args.workload == "cartpole_bnn_b4096" else None
-        roofline = {"bound": "tensor", "kernel": ["bnn_mlp (linearise rows)", "bnn_mlp (rollout rows)"][dom],
-                    "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                    "traffic": traffic, "peak_source": "bf16 dense sustained, " + peak_src,
-                    "tensor_passes_per_product": 3,
-                    "frac_of_fp32_accurate_bound": 3.0 * achieved / tensor_peak,
-                    "note": "fp32-accurate products on the tensor core cost 3 FP16 passes (a0*b0 + a0*b1 + a1*b0), "
-                            "so `frac` of the 16-bit dense peak cannot exceed 1/3; tensor pipe 63 % active, shared-memory "
-                            "data pipe 98 %, and the tile's layer-0 -> mid-stage -> layer-1 -> epilogue dependency chain "
-                            "plus the 1 kW power cap set the time (profiles/r1_summary.md section 5)",
-                    "flops_per_launch": flops, "avg_launch_ms": pms[dom] / pcnt[dom],
-                    "mlp_share_of_step": (pms[0] + pms[1]) / (ms / args.steps), "kernels": kinds}
-    else:
-        nz, nu = solver.nz, solver.nu      # linearise writes + backward reads/writes + rollout reads/writes
-        elems = (2 * nz * nz + 2 * nz * nu + 2 * nz + nu + nu * nu + 1 + nu) + (
-            2 * nz * nz + 2 * nz * nu + nz + nu + nu * nu + nu + nu * nz) + (nz + 2 * nu + nu * nz) + (nz + nu)
-        bytes_per_step = elems * (4 if dtype == torch.float32 else 8) * w["B"] * w["N"]
-        achieved = bytes_per_step / (ms / args.steps * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "whole pass (linearise+backward+rollout+accept)", "achieved": achieved,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                    "peak_source": peak_src}
 
-    # ---- final gather of the results over NCCL (outside the timed iteration) ---------------------
-    gather_ms = None
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cartpole_bnn_b4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads / strong sub-records")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    from pddp_b200 import sharding
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        out = [torch.empty_like(solver.view("U").contiguous()) for _ in range(world)] if rank == 0 else None
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        dist.gather(solver.view("U").contiguous(), out, dst=0)
-        torch.cuda.synchronize(dev)
-        gather_ms = (time.perf_counter() - t0) * 1e3
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    peaks = measured_peaks()
 
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        sec = time_oracle(w, torch.float32, 1)
-        cpu = {"value": w["N"] / sec, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
-               "sample": "1 problem x 1 iteration of the same workload (%.1f s); the reference handles one "
-                         "problem at a time" % sec}
+    rec = measure(args.workload, dtype, args.steps, args.warmup, dev, rank, world, dist)
+    roofline = roofline_record(args.workload, rec, dtype, peaks)
+    e2e = measure_e2e(args.workload, rec, dtype, args.steps, dev, world, dist)
+
+    # ---- final exchange of the results over NCCL (outside the timed iteration): Z, U, J, state in one all-gather,
+    #      timed with CUDA events AFTER a first call has set the channels up -----------------------------------
+    gather = None
+    if world > 1:
+        s = rec["solver"]
+        parts = [s.view("Z").contiguous(), s.view("U").contiguous(), s.J_opt, s.state]
+        sharding.all_gather_problems(parts, world * w["B"])
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = sharding.all_gather_problems(parts, world * w["B"])
+        g1.record()
+        torch.cuda.synchronize(dev)
+        gms = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        nbytes = sum(t.numel() * t.element_size() for t in parts)
+        gather = {"ms": float(gms.item()), "bytes_per_rank": nbytes, "tensors": "Z, U, J, state",
+                  "gbs_per_rank_received": (world - 1) * nbytes / (float(gms.item()) * 1e-3) / 1e9,
+                  "rows_gathered": int(full[0].shape[0])}
+        del full
+    del rec["solver"], rec["step"]
+    torch.cuda.empty_cache()
+
+    # ---- strong scaling: configs[1]'s 4096 problems split over the ranks -----------------------------------------
+    strong = None
+    if world > 1 and not args.no_others:
+        total_B = WORKLOADS[args.workload]["B"]
+        lo_, hi_ = sharding.shard_bounds(total_B, world, rank)
+        r2 = measure(args.workload, dtype, max(3, args.steps // 2), 3, dev, rank, world, dist, B=hi_ - lo_, profile=False)
+        strong = {"problems_total": total_B, "problems_per_gpu": hi_ - lo_, "ms_per_step": r2["ms_per_step"],
+                  "value": total_B * w["N"] / (r2["ms_per_step"] * 1e-3), "unit": "trajectory-steps/s", "scaling": "strong"}
+        del r2
+        torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations, a few steps each (single GPU only) -----------------------------------
+    others = None
+    if world == 1 and not args.no_others:
+        others = []
+        for name, dt in OTHER_WORKLOADS:
+            if name == args.workload and dt == args.dtype:
+                continue
+            d = torch.float32 if dt == "f32" else torch.float64
+            try:
+                r = measure(name, d, 3, 3, dev, 0, 1, dist)
+                rf = roofline_record(name, r, d, peaks)
+                others.append({"workload": name, "dtype": dt, "config": workload_config(name, r["w"]),
+                               "ms_per_step": r["ms_per_step"], "value": r["value"], "unit": "trajectory-steps/s",
+                               "steps": 3, "warmup": 3, "gpu_launches": r["launches"], "not_pd_problems": r["not_pd"],
+                               "roofline": {k: v for k, v in rf.items() if k != "note"}})
+                del r
+            except Exception as exc:                          # a sub-record must never take the headline line down
+                others.append({"workload": name, "dtype": dt, "error": "%s: %s" % (type(exc).__name__, exc)})
+            torch.cuda.empty_cache()
+
+    cpu = cpu_baseline_record(w) if rank == 0 and not args.no_cpu_baseline else None
     if rank == 0:
-        line = {"metric": "trajectory-steps/s", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        line = {"metric": "trajectory-steps/s", "value": rec["value"], "unit": "trajectory-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": workload_config(args.workload, w), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "not_pd_problems": not_pd, "final_gather_ms": gather_ms}
+                "config": workload_config(args.workload, w), "clocks": rec["clocks"], "e2e": e2e,
+                "gpu_launches": rec["launches"], "roofline": roofline, "cpu_baseline": cpu,
+                "not_pd_problems": rec["not_pd"], "final_gather": gather, "strong": strong, "other_workloads": others}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -268,8 +268,11 @@ int pddp_bnn_train(const pddp_bnn_train_config* cfg, const void* X, const void* 
 /* ---- instrumentation (bench.py) -----------------------------------------------------------------
  * pddp_profile_enable(1) makes the BNN path bracket its kernels with CUDA events on the launch
  * stream; pddp_profile_read synchronises and returns total milliseconds / launch counts for
- * kind 0 = MLP (linearise), 1 = MLP (rollout), 2 = moment matching (linearise), 3 = rollout step.
+ * kind 0 = MLP (linearise), 1 = MLP (rollout), 2 = moment matching (linearise), 3 = rollout step,
+ * 4 = backward pass, 5 = cost derivatives, 6 = linearise (known dynamics), 7 = rollout (known dynamics),
+ * 8 = accept / copy; `ms` and `count` must hold PDDP_PROFILE_KINDS entries.
  * pddp_launch_count() = kernels launched by this library since load.                          */
+#define PDDP_PROFILE_KINDS 9
 void pddp_profile_enable(int on);
 int pddp_profile_read(double* ms, int64_t* count);
 int64_t pddp_launch_count(void);

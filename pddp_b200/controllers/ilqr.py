@@ -120,14 +120,15 @@ class iLQRController(Controller):
         return s.state.clone() if self._batched else iLQRState(int(s.state[0]))
 
     def fit(self, U, encoding=StateEncoding.DEFAULT, n_iterations=50, tol=5e-6, max_reg=1e10, batch_rollout=True,
-            quiet=False, on_iteration=None, u_min=None, u_max=None, z0=None, shard=None, **kwargs):
+            quiet=False, on_iteration=None, u_min=None, u_max=None, z0=None, shard=None, max_passes=None, **kwargs):
         """ref: pddp/controllers/ilqr.py:237-316.  U: [N, nu] (z0 read from env.get_state() unless
         given) or [B, N, nu] with z0 [B, nz].  Returns (Z, U, state).
 
         Multi-GPU: with torch.distributed initialised (one process per GPU under torchrun) and a
         batched call, every rank passes the SAME full batch; each optimises its contiguous share of the problems
         -- no collective inside the iteration -- and ONE all-gather at the end gives every rank the full
-        (Z, U, K, state).  shard=False keeps the whole batch on this rank."""
+        (Z, U, K, state).  shard=False keeps the whole batch on this rank.  max_passes bounds the number of
+        whole-batch passes (a pass = linearise / backward / rollout / accept for every problem still in play)."""
         _lib.require_cuda(U, "U")
         self._batched = U.dim() == 3
         Ub = (U if self._batched else U.unsqueeze(0)).detach()
@@ -155,7 +156,7 @@ class iLQRController(Controller):
                     it[0] += 1
 
         s.fit(zb, Ub, n_iterations=n_iterations, tol=tol, max_reg=max_reg, u_min=u_min, u_max=u_max,
-              alphas=fit_alphas(U.dtype), on_pass=on_pass)
+              alphas=fit_alphas(U.dtype), on_pass=on_pass, max_passes=max_passes)
         if bool((s.state == int(iLQRState.MAX_REG)).any()):
             warnings.warn("exceeded max regularization term")
         if not sharded:

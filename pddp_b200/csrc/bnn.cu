@@ -669,7 +669,10 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
     cd.lLuz = make_layout(ly, B, N, nu * nz); cd.lLuu = make_layout(ly, B, N, nu * nu);
     note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 9 : 5) + 2 + 3LL * N + 2 + (s->enc == PDDP_ENC_FULL_COVARIANCE_MATRIX ? 1 : 0)
                   + (mode != PDDP_BNN_INPUT_INFER ? N - 1 : 0));
-    return cost_derivatives<T>(s->geo, s->enc, cd, c.st);
+    prof_begin(PROF_COST, c.st);
+    cudaError_t ce = cost_derivatives<T>(s->geo, s->enc, cd, c.st);
+    prof_end(PROF_COST, c.st);
+    return ce;
 }
 
 struct BnnRollCall {

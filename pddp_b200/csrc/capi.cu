@@ -90,17 +90,26 @@ static int linearize_known_t(const pddp_shape* s, const pddp_known_dynamics* dyn
     if (s->geo == GEO_RENDEZVOUS) {             // linear-quadratic: dynamics and cost derivatives in one kernel
         a.U_clamped = nullptr;
         note_launches(1);
-        return cuda_result(linearize_lq<T>(s->enc, a, st), "pddp_linearize_known(rendezvous)");
+        prof_begin(PROF_LIN_KNOWN, st);
+        cudaError_t e = linearize_lq<T>(s->enc, a, st);
+        prof_end(PROF_LIN_KNOWN, st);
+        return cuda_result(e, "pddp_linearize_known(rendezvous)");
     }
     a.U_clamped = s->enc == PDDP_ENC_IGNORE_UNCERTAINTY ? nullptr : (T*)L_u;
-    if (int e = cuda_result(linearize_known<T>(s->geo, s->enc, a, st), "pddp_linearize_known")) return e;
+    prof_begin(PROF_LIN_KNOWN, st);
+    cudaError_t le = linearize_known<T>(s->geo, s->enc, a, st);
+    prof_end(PROF_LIN_KNOWN, st);
+    if (int e = cuda_result(le, "pddp_linearize_known")) return e;
     note_launches(s->enc == PDDP_ENC_IGNORE_UNCERTAINTY ? 1 : 3);
     if (s->enc == PDDP_ENC_IGNORE_UNCERTAINTY) return 0;
     CostDerivArgs<T> c;
     c.B = s->B; c.N = s->N; c.cost = a.cost; c.Z = a.Z; c.U = (const T*)L_u; c.active = active;
     c.L = a.L; c.L_z = a.L_z; c.L_u = a.L_u; c.L_zz = a.L_zz; c.L_uz = a.L_uz; c.L_uu = a.L_uu; c.J_opt = a.J_opt;
     c.lZ = a.lZ; c.lU = a.lU; c.lL = a.lL; c.lLz = a.lLz; c.lLu = a.lLu; c.lLzz = a.lLzz; c.lLuz = a.lLuz; c.lLuu = a.lLuu;
-    return cuda_result(cost_derivatives<T>(s->geo, s->enc, c, st), "pddp_linearize_known(cost)");
+    prof_begin(PROF_COST, st);
+    cudaError_t ce = cost_derivatives<T>(s->geo, s->enc, c, st);
+    prof_end(PROF_COST, st);
+    return cuda_result(ce, "pddp_linearize_known(cost)");
 }
 
 extern "C" int pddp_linearize_known(const pddp_shape* s, const pddp_known_dynamics* dyn, const pddp_cost* cost,
@@ -159,7 +168,10 @@ static int backward_t(const pddp_shape* s, const void* F_z, const void* F_u, con
     a.lLuu = make_layout(ly, B, N, nu * nu); a.lU = make_layout(ly, B, N, nu);
     a.lk = make_layout(ly, B, N, nu); a.lK = make_layout(ly, B, N, nu * nz);
     note_launches(1);
-    return cuda_result(backward_pass<T>(a, s->layout, st), "pddp_backward");
+    prof_begin(PROF_BACKWARD, st);
+    cudaError_t e = backward_pass<T>(a, s->layout, st);
+    prof_end(PROF_BACKWARD, st);
+    return cuda_result(e, "pddp_backward");
 }
 
 extern "C" int pddp_backward(const pddp_shape* s, const void* F_z, const void* F_u, const void* L_z,
@@ -195,8 +207,10 @@ static int rollout_known_t(const pddp_shape* s, const pddp_known_dynamics* dyn, 
     a.lZ = make_layout(ly, B, N + 1, nz); a.lU = make_layout(ly, B, N, nu);
     a.lk = make_layout(ly, B, N, nu); a.lK = make_layout(ly, B, N, nu * nz);
     note_launches(2);
-    if (s->geo == GEO_RENDEZVOUS) return cuda_result(rollout_lq<T>(s->enc, a, st), "pddp_rollout_known(rendezvous)");
-    return cuda_result(rollout_known<T>(s->geo, s->enc, a, st), "pddp_rollout_known");
+    prof_begin(PROF_ROLL_KNOWN, st);
+    cudaError_t e = s->geo == GEO_RENDEZVOUS ? rollout_lq<T>(s->enc, a, st) : rollout_known<T>(s->geo, s->enc, a, st);
+    prof_end(PROF_ROLL_KNOWN, st);
+    return cuda_result(e, "pddp_rollout_known");
 }
 
 extern "C" int pddp_rollout_known(const pddp_shape* s, const pddp_known_dynamics* dyn, const pddp_cost* cost,
@@ -231,7 +245,10 @@ static int accept_t(const pddp_shape* s, const void* J_new, const int32_t* bw_st
     a.K = (const T*)K; a.K_nominal = (T*)K_nominal;
     a.lK = make_layout(s->layout, s->B, s->N, s->nu * s->nz);
     note_launches(2);
-    return cuda_result(accept_update<T>(a, accepted, st), "pddp_accept_update");
+    prof_begin(PROF_ACCEPT, st);
+    cudaError_t e = accept_update<T>(a, accepted, st);
+    prof_end(PROF_ACCEPT, st);
+    return cuda_result(e, "pddp_accept_update");
 }
 
 extern "C" int pddp_accept_update(const pddp_shape* s, const void* J_new, const int32_t* bw_status,

@@ -5,7 +5,7 @@
 namespace pddp {
 static bool g_on = false;
 static std::vector<cudaEvent_t> g_ev[PROF_KINDS];
-static size_t g_used[PROF_KINDS] = {0, 0, 0, 0};
+static size_t g_used[PROF_KINDS] = {};
 static long long g_launches = 0;
 
 static cudaEvent_t next_event(int kind) {

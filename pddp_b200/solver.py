@@ -242,10 +242,11 @@ class BatchedSolver:
 
     # ---------------------------------------------------------------- setup
     def set_problem(self, z0, U, u_min=None, u_max=None, alphas=None, iterations=1):
-        z0 = torch.as_tensor(z0).detach()
+        # (no torch.as_tensor on tensors: under torch.set_default_device it would MOVE them to the default device)
+        z0 = (z0 if isinstance(z0, torch.Tensor) else torch.as_tensor(z0)).detach()
         _lib.require_cuda(z0, "z0")
         self.z0.copy_(z0.reshape(self.B, self.nz))
-        self.store("U", torch.as_tensor(U).detach())
+        self.store("U", (U if isinstance(U, torch.Tensor) else torch.as_tensor(U)).detach())
         if (u_min is None) != (u_max is None):
             raise ValueError("u_min and u_max must be given together")
         self.u_min = expand_bound(u_min, self.nu, self.dtype, self.device)

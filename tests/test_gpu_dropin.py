@@ -22,7 +22,7 @@ def pddp():
 def cuda_default():
     torch.set_default_device("cuda")
     yield
-    torch.set_default_device("cpu")
+    torch.set_default_device(None)          # back to "no default-device mode" (not the same as "cpu")
 
 
 def test_reference_module_paths_resolve(pddp):
@@ -255,19 +255,27 @@ def test_gains_of_the_last_accepted_step_survive_max_reg(pddp):
     enc = O.IGNORE_UNCERTAINTY
     solver = O.ILQR(odyn, ocost, enc)
     trace = []
-    Zo, Uo, so = solver.fit(z0, U, n_iterations=60, max_reg=1e3, trace=trace)
+    # tol = 0: never "converged"; at the numerical optimum every candidate is rejected and mu escalates to max_reg
+    Zo, Uo, so = solver.fit(z0, U, n_iterations=100, tol=0.0, max_reg=1e2, trace=trace)
     assert so == O.MAX_REG and any(t[0] == O.ACCEPTED for t in trace), "the scenario must accept, then run out of reg"
     ctrl = pddp.controllers.iLQRController(None, model, cost)
     with _maybe_warns():
-        Z, Uc, state = ctrl.fit(U.cuda(), encoding=pddp.StateEncoding(enc), n_iterations=60, max_reg=1e3, z0=z0.cuda(),
-                                quiet=True)
+        Z, Uc, state = ctrl.fit(U.cuda(), encoding=pddp.StateEncoding(enc), n_iterations=100, tol=0.0, max_reg=1e2,
+                                z0=z0.cuda(), quiet=True)
     assert int(state) == O.MAX_REG
-    assert float((ctrl._K.cpu() - solver.K).abs().max()) <= 1e-6 * max(1.0, float(solver.K.abs().max()))
-    assert float((Uc.cpu() - Uo).abs().max()) <= 1e-6 * max(1.0, float(Uo.abs().max()))
-    # the feedback law away from the nominal state uses those gains (ilqr.py:339-354)
+    # (accept / reject at the optimum is decided at the rounding level, so the two runs may accept a different
+    # number of noise-level steps: the gains agree to the size of the last accepted mu, not to 1e-12)
+    scale = max(1.0, float(solver.K.abs().max()))
+    assert float((ctrl._K.cpu() - solver.K).abs().max()) <= 1e-4 * scale
+    assert float((Uc.cpu() - Uo).abs().max()) <= 1e-4 * max(1.0, float(Uo.abs().max()))
+    # ... and they are NOT the gains of the last backward pass, which ran with mu ~ max_reg
+    last_pass_K = ctrl._solver.matrices("K")[0].cpu()
+    assert float((last_pass_K - solver.K).abs().max()) > 1e-2 * scale
+    # the feedback law away from the nominal state uses the accepted gains (ilqr.py:339-354)
     dz = torch.tensor([0.05, -0.03], dtype=dtype)
     u = ctrl(Z[4] + dz.cuda(), 4, pddp.StateEncoding(enc))
-    assert torch.allclose(u.cpu(), Uo[4] + solver.K[4] @ dz, atol=1e-8)
+    assert torch.allclose(u.cpu(), Uc[4].cpu() + ctrl._K[4].cpu() @ dz, atol=1e-10)
+    assert torch.allclose(u.cpu(), Uo[4] + solver.K[4] @ dz, atol=1e-4)
 
 
 def test_scalar_bound_broadcasts_over_action_size_4(pddp):

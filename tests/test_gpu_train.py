@@ -14,7 +14,12 @@ def _model(fx, P):
     from pddp_b200.models.bnn import BDropout, bnn_dynamics_model_factory
     hidden = [int(h) for h in fx["hidden"]]
     kwargs = {} if int(fx["dropout"]) == 0 else {"dropout_layers": BDropout, "initial_p": fx["rate"]}
-    model = bnn_dynamics_model_factory(4, 1, hidden, [2], [0, 1, 3], **kwargs)(n_particles=10).to(fx["dtype"])
+    default = torch.get_default_dtype()
+    torch.set_default_dtype(fx["dtype"])          # like the reference run: temperature = 0.1 in the run's own precision
+    try:
+        model = bnn_dynamics_model_factory(4, 1, hidden, [2], [0, 1, 3], **kwargs)(n_particles=10)
+    finally:
+        torch.set_default_dtype(default)
     model._store_flat(fx["p_init"])
     return model
 
@@ -77,8 +82,6 @@ def test_training_with_the_device_generator_learns():
     assert float(model.model.drop_0.logit_p) != lp_before                      # concrete dropout rate is learned
     assert model.X_mean.shape == (6,) and model.model.fc_0.weight.device.type == "cpu"   # parameters written back in place
     # same seed, same run -> bit-identical parameters (counter-based noise, no atomics on the gradient path)
-    model2 = bnn_dynamics_model_factory(4, 1, [200, 200], [2], [0, 1, 3])(n_particles=50)
-    model2.load_state_dict(model.state_dict(), strict=False)
     a = bnn_dynamics_model_factory(4, 1, [64, 64], [2], [0, 1, 3])(n_particles=8)
     b = bnn_dynamics_model_factory(4, 1, [64, 64], [2], [0, 1, 3])(n_particles=8)
     b._store_flat(a.flat_parameters())

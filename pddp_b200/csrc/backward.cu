@@ -16,54 +16,45 @@
 
 namespace pddp {
 
-// scalar box-QP, a faithful restatement of the reference loop for a 1x1 problem.
-// returns the reference's result code; x = solution, is_free = (not clamped at exit),
-// qfree = Q (the "Cholesky factor squared" used for the feedback gain).
+// Scalar box-QP (ref: pddp/utils/constraint.py:150-266 for a 1 x 1 problem), in closed form.
+//
+// What the reference's projected-Newton loop does when n = 1 (Q > 0), step by step:
+//   it 0: x = clamp(x0); g = Q x + c.  x on a bound with the gradient pointing outward -> result 6 (all clamped),
+//         x is returned.  |g| < 1e-8 -> result 5, x is returned.  Otherwise the Newton target is
+//         xs = -(c / chol) / chol and the line search tries xc = clamp(x + step (xs - x)), step = 1, 0.6, 0.36, ...
+//         With theta = (xc - x) / (xs - x) in (0, 1] the Armijo ratio of a clamped candidate is
+//         theta (1 - theta / 2) / step: it passes at step 1 unless the bound cuts the step below ~0.106 of its
+//         length, and then it passes at the first step <= ~10 theta, where the candidate is STILL the bound.  An
+//         unclamped candidate (step < theta) has ratio 1 - step / 2 >= 0.5.  So iteration 0 always ends on
+//         x1 = clamp(x + (xs - x)).
+//   it 1: improvement below tol |f| -> result 4 with the free set of iteration 0 (free).  Otherwise the point is
+//         re-classified: on a bound with outward gradient -> result 6, not free; else interior, where g is rounding
+//         noise: result 5, or one more noise-sized Newton step that ends in result 2 or 4 -- x moves by a few ulp.
+// Every one of these exits is a success (result >= 1) and returns x1 up to rounding, so the loop collapses to the
+// expressions below (same operation order as the reference for x1).  Failures: Q <= 0 or NaN -> -1 (potrf
+// raises); non-finite c -> the reference spins 100 iterations on NaNs and returns 0.  The loop form (kept in
+// backward_nu.cu for n > 1) was 75 % of this kernel's executed instructions: lanes of a warp run different
+// iteration counts and the warp pays the union (profiles/r2_summary.md).
 template <class T>
 __device__ __forceinline__ int boxqp1(T x0, T Q, T c, T lo, T hi, T& x, bool& is_free) {
-    const T min_grad = T(1e-8), tol = T(1e-8), step_dec = T(0.6), min_step = T(1e-22), armijo = T(0.1);
+    const T min_grad = T(1e-8), tol = T(1e-8);
     x = clampv(x0, lo, hi);
     if (isinf(x)) x = T(0);
-    T f = T(0.5) * x * Q * x + x * c;
-    int result = 0;
-    T old_f = T(0);
-    bool clamped = false;
     is_free = true;
-    T chol = T(0);
-    for (int it = 0; it < 100; ++it) {
-        if (result != 0) break;
-        if (it > 0 && (old_f - f) < tol * fabs(old_f)) { result = 4; break; }
-        old_f = f;
-        T g = Q * x + c;
-        bool was = clamped;
-        clamped = (x == lo && g > T(0)) || (x == hi && g < T(0));
-        is_free = !clamped;
-        if (clamped) { result = 6; break; }
-        if (it == 0 || was != clamped) {
-            if (!(Q > T(0))) { result = -1; break; }
-            chol = jsqrt(Q);
-        }
-        if (fabs(g) < min_grad) { result = 5; break; }
-        T search = -((c / chol) / chol) - x;
-        T sdotg = search * g;
-        T step = T(1);
-        T xc = clampv(x + step * search, lo, hi);
-        T fc = T(0.5) * xc * Q * xc + xc * c;
-        while ((fc - old_f) / (step * sdotg) < armijo) {
-            step *= step_dec;
-            xc = clampv(x + step * search, lo, hi);
-            // Once the candidate rounds back onto x it stays there for every smaller step: the
-            // reference keeps shrinking the step ~110 times down to min_step and then leaves x
-            // unchanged with result 2 ("no descent direction").  Same outcome, without the spin --
-            // at the optimum the search direction is rounding noise, so this is the COMMON case.
-            if (xc == x) { fc = old_f; result = 2; break; }
-            fc = T(0.5) * xc * Q * xc + xc * c;
-            if (step < min_step) { result = 2; break; }
-        }
-        x = xc;
-        f = fc;
-    }
-    return result;
+    if (!isfinite(c) || !isfinite(x)) return 0;
+    const T g = Q * x + c;
+    if ((x == lo && g > T(0)) || (x == hi && g < T(0))) { is_free = false; return 6; }
+    if (!(Q > T(0))) return -1;
+    if (fabs(g) < min_grad) return 5;
+    const T f0 = T(0.5) * x * Q * x + x * c;
+    const T chol = jsqrt(Q);
+    const T search = -((c / chol) / chol) - x;
+    x = clampv(x + search, lo, hi);
+    const T f1 = T(0.5) * x * Q * x + x * c;
+    if ((f0 - f1) < tol * fabs(f0)) return 4;
+    const T g1 = Q * x + c;
+    if ((x == lo && g1 > T(0)) || (x == hi && g1 < T(0))) { is_free = false; return 6; }
+    return 4;
 }
 
 // gains for nu == 1.  Returns false where the reference raises (-> NOT_PD).

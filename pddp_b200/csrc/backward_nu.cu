@@ -15,18 +15,27 @@
 // Roofline: HBM -- per trajectory-step 2nz^2+2nz*nu+nz+nu+nu^2 elements read, nu+nu*nz written.
 #include "core.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace pddp {
 
 constexpr int MNU = MAX_NU;
 
+// TEAM threads own one problem: a whole CTA (256), a warp (32), or a SUB-WARP team of 4 / 8 / 16 lanes -- several
+// problems per warp, so the team-uniform scalar algebra (Jacobi sweeps, box-QP Newton iterations) that every lane
+// executes redundantly is paid once per 8 / 4 / 2 problems instead of once per problem, and with the
+// BATCH_INNER layout the lanes that hold the same element of consecutive problems read full 32-byte sectors.
+template <int TEAM>
+__device__ __forceinline__ unsigned nu_team_mask() {
+    return TEAM >= 32 ? 0xffffffffu : (((1u << (TEAM & 31)) - 1u) << ((threadIdx.x & 31) / TEAM * TEAM));
+}
 template <int TEAM>
 __device__ __forceinline__ void nu_team_sync() {
-    if (TEAM == 32) __syncwarp(); else __syncthreads();
+    if (TEAM <= 32) __syncwarp(nu_team_mask<TEAM>()); else __syncthreads();
 }
 template <int TEAM>
 __device__ __forceinline__ bool nu_team_any(bool x) {
-    if (TEAM == 32) return __any_sync(0xffffffffu, x);
+    if (TEAM <= 32) return __any_sync(nu_team_mask<TEAM>(), x);
     return __syncthreads_or(x) != 0;
 }
 
@@ -241,7 +250,7 @@ __host__ __device__ inline int backward_nu_elems(int nz, int nu) {
 }
 
 template <class T, int TEAM>
-__global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_nu_kernel(const BackwardArgs<T> a) {
+__global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM) backward_nu_kernel(const BackwardArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x % TEAM, warp = threadIdx.x / TEAM, wpb = blockDim.x / TEAM;
     const int b = blockIdx.x * wpb + warp;
@@ -331,25 +340,55 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_nu_kernel(co
             }
         }
         if (!finite) { ok = false; break; }                    // linalg.eig raises on NaN / Inf
-        jacobi_eig(nu, A, E, ev);
+        // Eigen-clipping (ilqr.py:631-634) only changes Q_uu when it has a negative eigenvalue.  A Cholesky
+        // factorisation of Q_uu that succeeds proves there is none: then E diag(e + reg) E^T is Q_uu + reg I and
+        // (E / (e + reg)) E^T its inverse, and the Jacobi sweeps (most of this kernel's team-uniform scalar work)
+        // are skipped.  Indefinite Q_uu (early iterations, small mu) takes the eigen route.
+        const unsigned all_dims = (1u << nu) - 1u;
+        bool pd;
+        {
+            T Uc[MNU][MNU];
+            pd = masked_chol(Quu, all_dims, Uc);
+        }
+        if (!pd) {
+            jacobi_eig(nu, A, E, ev);
 #pragma unroll
-        for (int i = 0; i < MNU; ++i) {
-            if (ev[i] < T(0)) ev[i] = T(1e-12);                // ref: ilqr.py:633-634
-            ev[i] += reg;
+            for (int i = 0; i < MNU; ++i) {
+                if (ev[i] < T(0)) ev[i] = T(1e-12);            // ref: ilqr.py:633-634
+                ev[i] += reg;
+            }
         }
         T kt[MNU];
         T M[MNU][MNU];                                         // K = -M Q_uz   (M = regularised inverse on the free dims)
         if (!bounded) {
+            if (pd) {                                          // M = (Q_uu + reg I)^-1 by Cholesky
+                T Qr[MNU][MNU], Ur[MNU][MNU];
 #pragma unroll
-            for (int i = 0; i < MNU; ++i)
+                for (int i = 0; i < MNU; ++i)
+#pragma unroll
+                    for (int j = 0; j < MNU; ++j) Qr[i][j] = Quu[i][j] + ((i == j && i < nu) ? reg : T(0));
+                masked_chol(Qr, all_dims, Ur);
 #pragma unroll
                 for (int j = 0; j < MNU; ++j) {
-                    T s = T(0);
+                    T r[MNU], x[MNU];
 #pragma unroll
-                    for (int m = 0; m < MNU; ++m)
-                        if (m < nu) s += (E[i][m] / ev[m]) * E[j][m];
-                    M[i][j] = (i < nu && j < nu) ? s : T(0);
+                    for (int i = 0; i < MNU; ++i) r[i] = (i == j && j < nu) ? T(1) : T(0);
+                    chol_solve(Ur, r, x);
+#pragma unroll
+                    for (int i = 0; i < MNU; ++i) M[i][j] = (i < nu && j < nu) ? x[i] : T(0);
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < MNU; ++i)
+#pragma unroll
+                    for (int j = 0; j < MNU; ++j) {
+                        T s = T(0);
+#pragma unroll
+                        for (int m = 0; m < MNU; ++m)
+                            if (m < nu) s += (E[i][m] / ev[m]) * E[j][m];
+                        M[i][j] = (i < nu && j < nu) ? s : T(0);
+                    }
+            }
 #pragma unroll
             for (int i = 0; i < MNU; ++i) {
                 T s = T(0);
@@ -368,9 +407,13 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_nu_kernel(co
 #pragma unroll
                 for (int j = 0; j < MNU; ++j) {
                     T s = T(0);
+                    if (pd) {
+                        s = (i < nu && j < nu) ? Quu[i][j] + (i == j ? reg : T(0)) : T(0);
+                    } else {
 #pragma unroll
-                    for (int m = 0; m < MNU; ++m)
-                        if (m < nu) s += (E[i][m] * ev[m]) * E[j][m];
+                        for (int m = 0; m < MNU; ++m)
+                            if (m < nu) s += (E[i][m] * ev[m]) * E[j][m];
+                    }
                     Qreg[i][j] = s;
                 }
             }
@@ -404,11 +447,11 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_nu_kernel(co
         nu_team_sync<TEAM>();
 #pragma unroll
         for (int i = 0; i < MNU; ++i) k_next[i] = kt[i];
-        if (lane < nu) {
+        for (int l = lane; l < nu; l += TEAM) {
             T kv = T(0);
 #pragma unroll
-            for (int i = 0; i < MNU; ++i) if (i == lane) kv = kt[i];
-            a.k[a.lk.at(b, t, lane)] = kv;
+            for (int i = 0; i < MNU; ++i) if (i == l) kv = kt[i];
+            a.k[a.lk.at(b, t, l)] = kv;
         }
         for (int e = lane; e < nz * nu; e += TEAM) {
             const int i = e / nz, c = e - i * nz;
@@ -457,6 +500,17 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_nu_kernel(co
     if (lane == 0) a.status[b] = ok ? 0 : 1;
 }
 
+template <class T, int TEAM>
+static cudaError_t launch_nu_teams(const BackwardArgs<T>& a, size_t per_team, cudaStream_t s) {
+    int tpb = 128 / TEAM;                                   // teams (problems) per CTA
+    while (tpb > 1 && per_team * tpb > 200 * 1024) tpb >>= 1;
+    const size_t smem = per_team * tpb;
+    cudaError_t e = cudaFuncSetAttribute(backward_nu_kernel<T, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    backward_nu_kernel<T, TEAM><<<(a.B + tpb - 1) / tpb, tpb * TEAM, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 template <class T>
 cudaError_t backward_pass_nu(const BackwardArgs<T>& a, cudaStream_t s) {
     if (a.nu < 1 || a.nu > MNU) return cudaErrorInvalidValue;
@@ -468,13 +522,15 @@ cudaError_t backward_pass_nu(const BackwardArgs<T>& a, cudaStream_t s) {
         backward_nu_kernel<T, 256><<<a.B, 256, per_team, s>>>(a);
         return cudaGetLastError();
     }
-    int wpb = 4;
-    while (wpb > 1 && per_team * wpb > 200 * 1024) wpb >>= 1;
-    const size_t smem = per_team * wpb;
-    cudaError_t e = cudaFuncSetAttribute(backward_nu_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    backward_nu_kernel<T, 32><<<(a.B + wpb - 1) / wpb, wpb * 32, smem, s>>>(a);
-    return cudaGetLastError();
+    // small states: sub-warp teams (nz <= 8: 4 lanes, 8 problems per warp; nz <= 12: 8 lanes).  PDDP_BACKWARD_NU_TEAM
+    // overrides the choice (A/B measurements).
+    static int forced_team = -1;
+    if (forced_team < 0) { const char* e = getenv("PDDP_BACKWARD_NU_TEAM"); forced_team = e ? atoi(e) : 0; }
+    const int team = forced_team ? forced_team : a.nz <= 8 ? 4 : a.nz <= 12 ? 8 : 32;
+    if (team == 4) return launch_nu_teams<T, 4>(a, per_team, s);
+    if (team == 8) return launch_nu_teams<T, 8>(a, per_team, s);
+    if (team == 16) return launch_nu_teams<T, 16>(a, per_team, s);
+    return launch_nu_teams<T, 32>(a, per_team, s);
 }
 template cudaError_t backward_pass_nu<float>(const BackwardArgs<float>&, cudaStream_t);
 template cudaError_t backward_pass_nu<double>(const BackwardArgs<double>&, cudaStream_t);

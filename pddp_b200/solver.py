@@ -168,7 +168,7 @@ class BatchedSolver:
         if self.device.type != "cuda":
             raise RuntimeError("pddp_b200 runs on CUDA devices only (no CPU fallback)")
         if layout is None:   # SoA for thread-per-problem kernels, records for warp-per-problem
-            layout = _lib.BATCH_INNER if (not dynamics.is_bnn and self.nz <= 6) else _lib.PROBLEM_MAJOR
+            layout = _lib.BATCH_INNER if (not dynamics.is_bnn and self.nz <= 8) else _lib.PROBLEM_MAJOR
         self.layout = layout
         self.shape = _lib.Shape(_lib.dtype_code(dtype), layout, self.geo, int(self.enc), self.B,
                                 self.N, self.nz, self.nu)

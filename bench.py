@@ -324,13 +324,20 @@ def stage_elements(nz, nu):
 
 
 def mlp_tile_flops(w):
-    """Tensor FLOPs the tcgen05 kernel EXECUTES per 128-row tile (bnn_mlp_tc.cuh): layer 1 = 3 split-FP16 passes of
-    M128 x N208 x K16 per 16-wide K-block of the (H0 + 1)-wide hidden vector (the +1 is the bias unit), layer 0 = 2
-    MMAs of M128 x N32 x K16 per 32-unit chunk.  Compare with the algorithmic 2 * MACs per row."""
-    H = w["hidden"]
-    nkb = (H + 1 + 15) // 16
-    chunks = (H + 1 + 31) // 32
-    return 2.0 * 128 * (3 * nkb * 208 * 16 + 2 * chunks * 32 * 16)
+    """Tensor FLOPs the tcgen05 kernel EXECUTES per 128-row tile, averaged over the particles (bnn_mlp_tc.cuh): for
+    particle p layer 1 = 3 split-FP16 passes of M128 x N(p) x K16 per K-block, with K(p) = kept layer-0 units + the
+    bias unit and N(p) = kept layer-1 units, both rounded up to 16 (units whose dropout mask is below 2^-24 are
+    compacted away); layer 0 = 2 (3 when the input needs 16 columns) MMAs of M128 x N32 x K16 per 32-unit chunk.
+    Compare with the algorithmic 2 * MACs per row."""
+    _, D, ang, _ = GEOMETRY[w["problem"]]
+    _, _, masks, _ = synth_bnn(w["problem"], w["P"], w["hidden"], seed=0)
+    compact = os.environ.get("PDDP_MLP_COMPACT", "1") != "0"
+    keep = [(m >= 2.0 ** -24) if compact else torch.ones_like(m, dtype=torch.bool) for m in masks]
+    nkb = (keep[0].sum(1) + 1 + 15) // 16
+    ncol = ((keep[1].sum(1) + 15) // 16 * 16).clamp_min(16)
+    l0_mmas = 2 if D + len(ang) + 2 <= 8 else 3
+    per_particle = 2.0 * 128 * (3 * nkb * ncol * 16 + l0_mmas * ((nkb + 1) // 2) * 32 * 16)
+    return float(per_particle.double().mean())
 
 
 def build_solver(name, dtype, dev, rank, B=None):

@@ -471,10 +471,13 @@ static Workspace<T> carve(void* base, const pddp_shape* s, const pddp_bnn* n, in
     w.J = take(S);
     w.Zall = take(S * (s->N + 1) * s->nz);
     w.Uall = take(S * s->N);
-    w.im.W1img = reinterpret_cast<unsigned char*>(take((size_t)tc::MAX_NKB * tc::B_STAGE / sizeof(T)));
+    w.im.W1img = reinterpret_cast<unsigned char*>(take(P * tc::W1_PSTRIDE / sizeof(T)));        // per-particle (compacted) images
     w.im.W0img = reinterpret_cast<unsigned char*>(take(P * (size_t)tc::Cfg<16, 8>::W0_BYTES / sizeof(T)));
     w.im.W2p = reinterpret_cast<float*>(take(P * (size_t)tc::TILE_N * 8 * sizeof(float) / sizeof(T)));
     w.im.scale = reinterpret_cast<float*>(take(256 / sizeof(T)));
+    w.im.meta = reinterpret_cast<int*>(take(P * (size_t)tc::META * sizeof(int) / sizeof(T) + 1));
+    w.im.idx0 = reinterpret_cast<int*>(take(P * (size_t)tc::TILE_N * sizeof(int) / sizeof(T)));
+    w.im.idx1 = reinterpret_cast<int*>(take(P * (size_t)tc::TILE_N * sizeof(int) / sizeof(T)));
     w.bytes = off;
     return w;
 }
@@ -513,19 +516,24 @@ static cudaError_t prep_weights(const pddp_shape* s, const pddp_bnn* n, const Wo
     bnn_transpose_kernel<T><<<16, 256, 0, st>>>((const T*)n->mask0, n->P, n->H0, n->P, w.m0T);
     bnn_transpose_kernel<T><<<16, 256, 0, st>>>((const T*)n->mask1, n->P, n->H1, n->P, w.m1T);
     if (use_tensor_cores<T>(n->H0, n->H1)) {
-        const int nkb = (n->H0 + 1 + tc::KB - 1) / tc::KB;
+        // PDDP_MLP_COMPACT=0 keeps every hidden unit (A/B measurements; the images are then the same for all particles)
+        static int compact = -1;
+        if (compact < 0) { const char* e = getenv("PDDP_MLP_COMPACT"); compact = (e && e[0] == '0') ? 0 : 1; }
+        int* meta = const_cast<int*>(w.im.meta);
+        tc::prep_index_kernel<<<(n->P + 63) / 64, 64, 0, st>>>((const float*)n->mask0, (const float*)n->mask1, n->P, n->H0, n->H1,
+                                                               compact, w.im.idx0, w.im.idx1, meta);
         tc::prep_scale_kernel<<<1, 256, 0, st>>>((const float*)n->W1, (const float*)n->b1, n->H0, n->H1,
                                                  const_cast<float*>(w.im.scale));
-        tc::prep_w1_kernel<<<64, 256, 0, st>>>((const float*)n->W1, (const float*)n->b1, n->H0, n->H1, nkb, w.im.scale,
-                                               const_cast<unsigned char*>(w.im.W1img));
+        tc::prep_w1_kernel<<<592, 256, 0, st>>>((const float*)n->W1, (const float*)n->b1, n->P, n->H0, n->H1, w.im.idx0, w.im.idx1,
+                                                meta, w.im.scale, const_cast<unsigned char*>(w.im.W1img));
         if (DA + 2 <= 8)
             tc::prep_w0_kernel<8><<<64, 256, 0, st>>>((const float*)n->W0, (const float*)n->b0, (const float*)n->mask0,
-                                                       n->P, n->H0, DA + 1, const_cast<unsigned char*>(w.im.W0img));
+                                                       n->P, n->H0, DA + 1, w.im.idx0, meta, const_cast<unsigned char*>(w.im.W0img));
         else
             tc::prep_w0_kernel<16><<<64, 256, 0, st>>>((const float*)n->W0, (const float*)n->b0, (const float*)n->mask0,
-                                                        n->P, n->H0, DA + 1, const_cast<unsigned char*>(w.im.W0img));
+                                                        n->P, n->H0, DA + 1, w.im.idx0, meta, const_cast<unsigned char*>(w.im.W0img));
         tc::prep_w2_kernel<<<64, 256, 0, st>>>((const float*)n->W2, (const float*)n->mask1, n->P, n->H1, D, D <= 4 ? 4 : 8,
-                                               w.im.scale, const_cast<float*>(w.im.W2p));
+                                               w.im.idx1, meta, w.im.scale, const_cast<float*>(w.im.W2p));
     }
     return cudaGetLastError();
 }
@@ -554,8 +562,9 @@ static cudaError_t launch_mlp_tc(const BnnMlpArgs<float>& a, const tc::Images& i
     const int S = (int)(a.total / a.net.P);                  // items per particle: (problem, alpha) pairs / problems
     const int tiles_p = (S + tc::TILE_M - 1) / tc::TILE_M;      // super-tiles per particle (TAN: 1 + T passes each)
     const long long ntiles = (long long)tiles_p * a.net.P;
+    if (ntiles >= (1ll << 31)) return cudaErrorInvalidValue;
     const int grid = (int)(ntiles < (long long)num_sms() ? ntiles : (long long)num_sms());
-    kern<<<grid, tc::THREADS, smem, st>>>(a, im, S, tiles_p, (a.net.H0 + 1 + tc::KB - 1) / tc::KB);
+    kern<<<grid, tc::THREADS, smem, st>>>(a, im, S, tiles_p);
     return cudaGetLastError();
 }
 template <class T, int GEO, bool TAN>
@@ -667,7 +676,7 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
     cd.lZ = lZ; cd.lU = lU; cd.lL = make_layout(ly, B, N + 1, 1); cd.lLz = make_layout(ly, B, N + 1, nz);
     cd.lLu = make_layout(ly, B, N, nu); cd.lLzz = make_layout(ly, B, N + 1, nz * nz);
     cd.lLuz = make_layout(ly, B, N, nu * nz); cd.lLuu = make_layout(ly, B, N, nu * nu);
-    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 9 : 5) + 2 + 3LL * N + 2 + (s->enc == PDDP_ENC_FULL_COVARIANCE_MATRIX ? 1 : 0)
+    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 10 : 5) + 2 + 3LL * N + 2 + (s->enc == PDDP_ENC_FULL_COVARIANCE_MATRIX ? 1 : 0)
                   + (mode != PDDP_BNN_INPUT_INFER ? N - 1 : 0));
     prof_begin(PROF_COST, c.st);
     cudaError_t ce = cost_derivatives<T>(s->geo, s->enc, cd, c.st);
@@ -735,7 +744,7 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     bnn_roll_select_kernel<T><<<(unsigned)(((long long)B * 32 + 127) / 128), 128, 0, c.st>>>(
         B, N, A, nz, w.J, w.Zall, w.Uall, c.active, c.bw_status, (T*)c.J_all, c.amin, (T*)c.J_new, (T*)c.Z_new,
         (T*)c.U_new, r.lZ, r.lU);
-    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 9 : 5) + 2 + 2LL * N + 1 + (mode != PDDP_BNN_INPUT_INFER ? N - 1 : 0));
+    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 10 : 5) + 2 + 2LL * N + 1 + (mode != PDDP_BNN_INPUT_INFER ? N - 1 : 0));
     return cudaGetLastError();
 }
 

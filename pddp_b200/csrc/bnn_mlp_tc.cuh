@@ -28,6 +28,14 @@
 //     chunk, ReLU / gate, hi-lo split, st.shared into the UMMA K-major layout) and one layer-1
 //     MMA-issuer thread; one polling layer-0 issuer thread for both tracks; one bulk-copy loader.
 //
+//   * per-particle COMPACTION: a hidden unit whose dropout mask is below 2^-24 (CDropout at temperature 0.1: ~16 % of
+//     the units of a particle; BDropout: every dropped unit) contributes less than fp32 rounding to anything
+//     downstream.  Tiles are particle-uniform, so such units are simply left out of that particle's images: the
+//     layer-1 GEMM of particle p is M128 x N(p) x K(p) with K(p) = kept layer-0 units + the bias unit (rounded up
+//     to 16) and N(p) = kept layer-1 units (rounded up to 16) -- typically 11 K-blocks x 176 columns instead of
+//     13 x 208, 0.72x the tensor work.  The W1 image is therefore per particle too, and the W1 stream the two
+//     tracks share is organised in SEGMENTS (runs of super-tiles of one particle inside the CTA's range).
+//
 // TMEM (512 columns): track t owns columns [256t, 256t+208) for the layer-1 accumulator and
 // [256t+208, 256t+240) for the layer-0 chunk.
 #pragma once
@@ -272,21 +280,51 @@ __global__ void prep_scale_kernel(const float* W1, const float* b1, int H0, int 
         scale[1] = ldexpf(1.f, -e);
     }
 }
-// W1 image: [nkb][208 rows x (b0[16] | b1[16]) fp16] SWIZZLE_64B, scaled; column H0 carries the bias b1.
-__global__ void prep_w1_kernel(const float* W1 /*[H1][H0]*/, const float* b1, int H0, int H1, int nkb,
-                               const float* scale, unsigned char* img) {
-    const int total = nkb * TILE_N * KB;
+// Per-particle compaction lists.  A unit is KEPT when its mask is >= DROP_BELOW (NaN masks are kept too): below
+// that its contribution is under half an ulp of any sum it enters.  idx0[p][q] / idx1[p][c] = q-th / c-th kept
+// unit of layer 0 / layer 1 (ascending), meta[p] = {K-blocks, accumulator columns, kept layer-0 units, kept
+// layer-1 units}: the K range is the kept layer-0 units followed by the bias unit, rounded up to 16.
+constexpr float DROP_BELOW = 5.9604645e-8f;    // 2^-24
+constexpr int META = 4;
+__global__ void prep_index_kernel(const float* mask0 /*[P][H0]*/, const float* mask1 /*[P][H1]*/, int P, int H0, int H1,
+                                  int compact, int* idx0 /*[P][TILE_N]*/, int* idx1 /*[P][TILE_N]*/, int* meta /*[P][META]*/) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    int n0 = 0, n1 = 0;
+    for (int n = 0; n < H0; ++n)
+        if (!compact || !(mask0[(size_t)p * H0 + n] < DROP_BELOW)) idx0[(size_t)p * TILE_N + n0++] = n;
+    for (int c = 0; c < H1; ++c)
+        if (!compact || !(mask1[(size_t)p * H1 + c] < DROP_BELOW)) idx1[(size_t)p * TILE_N + n1++] = c;
+    const int ncol = (n1 + 15) & ~15;
+    meta[p * META + 0] = (n0 + 1 + KB - 1) / KB;
+    meta[p * META + 1] = ncol < 16 ? 16 : ncol;
+    meta[p * META + 2] = n0;
+    meta[p * META + 3] = n1;
+}
+// W1 image of particle p: [K-block][N(p) rows x (b0[16] | b1[16]) fp16] SWIZZLE_64B, scaled; row c is kept layer-1
+// unit idx1[p][c], K position q is kept layer-0 unit idx0[p][q], position n0 (the bias unit) carries b1.  Blocks sit
+// B_STAGE bytes apart; only the first N(p) * 64 bytes of a block are read.
+constexpr size_t W1_PSTRIDE = (size_t)13 * 208 * 64;       // MAX_NKB * B_STAGE
+__global__ void prep_w1_kernel(const float* W1 /*[H1][H0]*/, const float* b1, int P, int H0, int H1, const int* idx0,
+                               const int* idx1, const int* meta, const float* scale, unsigned char* img) {
+    const long long total = (long long)P * MAX_NKB * TILE_N * KB;
     const float sc = scale[0];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int kb = i / (TILE_N * KB), rem = i - kb * TILE_N * KB;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i / (MAX_NKB * TILE_N * KB)), rem0 = (int)(i - (long long)p * (MAX_NKB * TILE_N * KB));
+        const int kb = rem0 / (TILE_N * KB), rem = rem0 - kb * TILE_N * KB;
         const int n = rem / KB, kk = rem - n * KB, k = kb * KB + kk;
+        const int nkb = meta[p * META], ncol = meta[p * META + 1], n0 = meta[p * META + 2], n1 = meta[p * META + 3];
+        if (kb >= nkb || n >= ncol) continue;
         float w = 0.f;
-        if (n < H1) w = k < H0 ? W1[(size_t)n * H0 + k] : (k == H0 ? b1[n] : 0.f);
+        if (n < n1) {
+            const int c = idx1[(size_t)p * TILE_N + n];
+            w = k < n0 ? W1[(size_t)c * H0 + idx0[(size_t)p * TILE_N + k]] : (k == n0 ? b1[c] : 0.f);
+        }
         w *= sc;
         const __half h0 = __float2half_rn(w);
         const __half h1 = __float2half_rn(w - __half2float(h0));
         // element kk of [b0 | b1] sits at 2-byte index kk (b0) or 16 + kk (b1) of the 64-byte row
-        unsigned char* row = img + (size_t)kb * B_STAGE + (n >> 3) * 512 + (n & 7) * 64;
+        unsigned char* row = img + (size_t)p * W1_PSTRIDE + (size_t)kb * B_STAGE + (n >> 3) * 512 + (n & 7) * 64;
         const int sw = (n >> 1) & 3;
         *reinterpret_cast<__half*>(row + (((kk >> 3) ^ sw) << 4) + (kk & 7) * 2) = h0;
         *reinterpret_cast<__half*>(row + (((2 + (kk >> 3)) ^ sw) << 4) + (kk & 7) * 2) = h1;
@@ -294,20 +332,22 @@ __global__ void prep_w1_kernel(const float* W1 /*[H1][H0]*/, const float* b1, in
 }
 // Per-particle layer-0 image: [P][chunk][X | Y][32 rows], split FP16 like layer 1: with w = b0 + b1 the row
 // of part X is [b0 | b0] and of part Y is [b1 | 0], so that against the operand row [a0 | a1]
-// X gives a0*b0 + a1*b0 and Y gives a0*b1.  Row n < H0 is m0[p][n]*[W0[n][:], b0[n]], row H0 is the unit
-// vector of the bias column (the constant-1 hidden unit), the rest zero.
+// X gives a0*b0 + a1*b0 and Y gives a0*b1.  Row q < n0(p) is m0[p][n]*[W0[n][:], b0[n]] of kept unit n = idx0[p][q],
+// row n0(p) is the unit vector of the bias column (the constant-1 hidden unit), the rest zero.
 template <int K0P>
 __global__ void prep_w0_kernel(const float* W0 /*[H0][K0]*/, const float* b0, const float* mask0 /*[P][H0]*/, int P,
-                               int H0, int K0, unsigned char* img) {
+                               int H0, int K0, const int* idx0, const int* meta, unsigned char* img) {
     typedef Cfg<K0P, 4> C;
     const int total = P * MAX_NCH * N0 * K0P;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int p = i / (MAX_NCH * N0 * K0P), rem = i - p * (MAX_NCH * N0 * K0P);
         const int j = rem / (N0 * K0P), rem2 = rem - j * (N0 * K0P);
-        const int rr = rem2 / K0P, k = rem2 - rr * K0P, n = j * N0 + rr;
+        const int rr = rem2 / K0P, k = rem2 - rr * K0P, q = j * N0 + rr, n0 = meta[p * META + 2];
         float w = 0.f;
-        if (n < H0) w = mask0[(size_t)p * H0 + n] * (k < K0 ? W0[(size_t)n * K0 + k] : (k == K0 ? b0[n] : 0.f));
-        else if (n == H0) w = k == K0 ? 1.f : 0.f;
+        if (q < n0) {
+            const int n = idx0[(size_t)p * TILE_N + q];
+            w = mask0[(size_t)p * H0 + n] * (k < K0 ? W0[(size_t)n * K0 + k] : (k == K0 ? b0[n] : 0.f));
+        } else if (q == n0) w = k == K0 ? 1.f : 0.f;
         const __half h0 = __float2half_rn(w);
         const __half h1 = __float2half_rn(w - __half2float(h0));
         unsigned char* base = img + (size_t)p * C::W0_BYTES + (size_t)j * C::W0_CHUNK;
@@ -321,7 +361,7 @@ __global__ void prep_w0_kernel(const float* W0 /*[H0][K0]*/, const float* b0, co
 // W2p[p][c / 2][o][c % 2] when D <= 4 (the epilogue's FFMA2 takes (column 2j, column 2j+1) of one output as a 64-bit
 // operand), as W2p[p][c][o] otherwise
 __global__ void prep_w2_kernel(const float* W2 /*[2D][H1]*/, const float* mask1 /*[P][H1]*/, int P, int H1, int D, int DP,
-                               const float* scale, float* out) {
+                               const int* idx1, const int* meta, const float* scale, float* out) {
     const bool pairs = D <= 4;
     const int total = P * TILE_N * DP;
     const float inv = scale[1];              // the layer-1 accumulator carries the W1 image's scale
@@ -329,27 +369,87 @@ __global__ void prep_w2_kernel(const float* W2 /*[2D][H1]*/, const float* mask1 
         const int p = i / (TILE_N * DP), rem = i - p * (TILE_N * DP);
         const int jp = rem / (2 * DP), rem2 = rem - jp * (2 * DP);
         const int o = pairs ? rem2 >> 1 : rem % DP, c = pairs ? 2 * jp + (rem2 & 1) : rem / DP;
-        out[i] = (c < H1 && o < D) ? mask1[(size_t)p * H1 + c] * W2[(size_t)o * H1 + c] * inv : 0.f;
+        float v = 0.f;                           // accumulator column c of particle p is kept layer-1 unit idx1[p][c]
+        if (c < meta[p * META + 3] && o < D) {
+            const int u = idx1[(size_t)p * TILE_N + c];
+            v = mask1[(size_t)p * H1 + u] * W2[(size_t)o * H1 + u] * inv;
+        }
+        out[i] = v;
     }
 }
 
 struct Images {
-    const unsigned char* W1img;
+    const unsigned char* W1img;   // [P] per-particle images, W1_PSTRIDE apart
     const unsigned char* W0img;
     const float* W2p;
     const float* scale;        // [2]: power-of-two scale of the W1 image and its inverse
+    const int* meta;           // [P][META]: K-blocks, accumulator columns, kept units of layer 0 / layer 1
+    int* idx0;                 // [P][TILE_N] compaction lists (prep kernels only)
+    int* idx1;
+};
+
+// ---- tile schedule ------------------------------------------------------------------------------------------
+// The CTA owns super-tiles [T0, T1) (tau = particle * tiles_p + item block).  A SEGMENT is the run of super-tiles of
+// one particle inside that range: within a segment track 0 takes the 1st, 3rd, ... and track 1 the 2nd, 4th, ...
+// super-tile, and the W1 stream carries that particle's image: len = max over the tracks of the blocks they
+// consume (track 1 starts `skew` blocks into the segment, so the epilogues of the two tracks interleave).
+struct Seg {
+    int ta, cnt, p, nkb, ncol, skew, n[2], len;
+};
+__device__ __forceinline__ bool seg_at(int ta, int T1, int tiles_p, const int* meta, int rpp, Seg& s) {
+    if (ta >= T1) return false;
+    s.ta = ta;
+    s.p = ta / tiles_p;
+    const int end = min((s.p + 1) * tiles_p, T1);
+    s.cnt = end - ta;
+    s.nkb = __ldg(meta + s.p * META);
+    s.ncol = __ldg(meta + s.p * META + 1);
+    s.skew = (s.nkb / 2) & ~1;
+    s.n[0] = ((s.cnt + 1) / 2) * rpp;
+    s.n[1] = (s.cnt / 2) * rpp;
+    const int len0 = s.n[0] * s.nkb, len1 = s.n[1] ? s.skew + s.n[1] * s.nkb : 0;
+    s.len = len0 > len1 ? len0 : len1;
+    return true;
+}
+// the super-tiles of ONE track, in order, across segments.  Three registers of state (the worker roles run at the
+// register cap): the kernel-uniform T1 / tiles_p / t / meta are passed in, particle and item block are recomputed
+// from tau where they are needed (once per tile).
+struct TrackIter {
+    int seg_end, tau, kn;                                     // kn = nkb | ncol << 8 of the current particle; tau < 0: done
+    __device__ __forceinline__ bool valid() const { return tau >= 0; }
+    __device__ __forceinline__ int nkb() const { return kn & 255; }
+    __device__ __forceinline__ int ncol() const { return kn >> 8; }
+    __device__ __forceinline__ int skew() const { return (nkb() / 2) & ~1; }
+    __device__ __forceinline__ int p(int tiles_p) const { return tau / tiles_p; }
+    __device__ __forceinline__ void locate(int seg_start, int T1, int tiles_p, int t, const int* meta) {
+        tau = -1;
+        while (seg_start < T1) {
+            const int pp = seg_start / tiles_p;
+            const int end = min((pp + 1) * tiles_p, T1);
+            if (seg_start + t < end) {
+                tau = seg_start + t; seg_end = end;
+                kn = __ldg(meta + pp * META) | (__ldg(meta + pp * META + 1) << 8);
+                return;
+            }
+            seg_start = end;
+        }
+    }
+    __device__ __forceinline__ void next(int T1, int tiles_p, int t, const int* meta) {
+        tau += 2;
+        if (tau >= seg_end) locate(seg_end, T1, tiles_p, t, meta);
+    }
 };
 
 template <int GEO, bool TAN>
 __global__ void __launch_bounds__(THREADS, 1)
-bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p, int nkb) {
+bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p) {
     typedef Geo<GEO> G;
     constexpr int D = G::D, DA = G::DA, NNA = G::NNA, NANG = G::NANG, K0 = DA + G::NU;
     constexpr int K0P = K0 + 1 <= 8 ? 8 : 16, DP = D <= 4 ? 4 : 8;
     typedef Cfg<K0P, DP> C;
     constexpr int NB = C::NB, NS = C::NS, ROWB0 = C::ROWB0;
     constexpr int TD = TAN ? D + G::NU : 0, RPP = 1 + TD;     // passes per super-tile: primal + one per tangent direction
-    constexpr uint32_t IDESC1 = idesc_f16(TILE_M, TILE_N), IDESC0 = idesc_f16(TILE_M, N0);
+    constexpr uint32_t IDESC0 = idesc_f16(TILE_M, N0);
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + C::ALIGN_PAD - 1) & ~(uintptr_t)(C::ALIGN_PAD - 1));
@@ -377,15 +477,8 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
     // pre-activations of the same (item, hidden unit) and the ReLU gate never crosses lanes.
     // Each CTA owns a contiguous range of super-tiles; track t takes every other one.  Track 1 is
     // `skew` K-blocks behind track 0 in the W1 stream.
-    const long long NT = (long long)P * tiles_p;
-    const long long T0 = NT * blockIdx.x / gridDim.x, T1 = NT * (blockIdx.x + 1) / gridDim.x;
-    const int cnt = (int)(T1 - T0);
-    const int ntl[2] = {((cnt + 1) / 2) * RPP, (cnt / 2) * RPP};     // MMA tiles per track
-    const int skew = (nkb / 2) & ~1;
-    const int nch = (nkb + 1) / 2;
-    const uint32_t w0_bytes = (uint32_t)nch * C::W0_CHUNK;
-    const int len0 = ntl[0] * nkb, len1 = ntl[1] ? skew + ntl[1] * nkb : 0;
-    const int nblk = len0 > len1 ? len0 : len1;          // W1 K-blocks this CTA streams
+    const long long NT = (long long)P * tiles_p;            // < 2^31 (checked by the launcher)
+    const int T0 = (int)(NT * blockIdx.x / gridDim.x), T1 = (int)(NT * (blockIdx.x + 1) / gridDim.x);
 
     if (tid == 0) {
         for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2); }   // both tracks release a W1 stage
@@ -410,16 +503,28 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register re-balancing between the roles (640 threads -> 96 registers per thread at launch): the warpgroup of
+    // the loader / issuer warps (16-19) needs ~40, the four worker warpgroups run at the cap and spilled (the
+    // tangent instantiations: gate words + packed accumulators + TMEM fragments).  56 x 128 + 104 x 512 <= 96 x 640.
+    // (The instruction sits at the top of each role's branch so that it dominates exactly that role's code.)
+    if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 18) {
         // ================= loader: W1 K-blocks, shared by both tracks =================
         if (lane == 0) {
-            uint32_t s = 0, ph = 1, kb = 0;
-            for (int nb = 0; nb < nblk; ++nb) {
-                mbar_wait(&b_empty[s], ph);
-                mbar_expect_tx(&b_full[s], B_STAGE);
-                bulk_g2s(smem + C::B_OFF + s * B_STAGE, im.W1img + (size_t)kb * B_STAGE, B_STAGE, &b_full[s]);
-                if (++s == NB) { s = 0; ph ^= 1; }
-                if (++kb == (uint32_t)nkb) kb = 0;
+            uint32_t s = 0, ph = 1;
+            Seg sg;
+            for (bool live = seg_at(T0, T1, tiles_p, im.meta, RPP, sg); live; live = seg_at(sg.ta + sg.cnt, T1, tiles_p, im.meta, RPP, sg)) {
+                const unsigned char* img = im.W1img + (size_t)sg.p * W1_PSTRIDE;
+                const uint32_t bytes = (uint32_t)sg.ncol * 64u;
+                int kb = 0;
+                for (int nb = 0; nb < sg.len; ++nb) {
+                    mbar_wait(&b_empty[s], ph);
+                    mbar_expect_tx(&b_full[s], bytes);
+                    bulk_g2s(smem + C::B_OFF + s * B_STAGE, img + (size_t)kb * B_STAGE, bytes, &b_full[s]);
+                    if (++s == NB) { s = 0; ph ^= 1; }
+                    if (++kb == sg.nkb) kb = 0;
+                }
             }
         }
     } else if (warp == 19) {
@@ -427,14 +532,21 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
         // issued the moment its mid-stage has drained chunk c, independent of where layer 1 stands ====
         if (lane == 0) {
             uint32_t l0cnt[2] = {0, 0}, w0loads[2] = {0, 0};
-            int curp[2] = {-1, -1}, k[2] = {0, 0}, pos[2] = {0, 0};
+            int curp[2] = {-1, -1}, k[2] = {0, 0}, pos[2] = {0, 0}, d[2] = {0, 0};   // k = tiles issued (track-global), d = pass
+            int tp[2];                             // particle of the track's current super-tile (a division: not in the poll loop)
             bool fresh[2] = {true, true};          // next chunk is the first of its tile
-            while (k[0] < ntl[0] || k[1] < ntl[1]) {
+            TrackIter it[2];
+            it[0].locate(T0, T1, tiles_p, 0, im.meta);
+            it[1].locate(T0, T1, tiles_p, 1, im.meta);
+            tp[0] = it[0].valid() ? it[0].p(tiles_p) : -1;
+            tp[1] = it[1].valid() ? it[1].p(tiles_p) : -1;
+            while (it[0].valid() || it[1].valid()) {
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    if (k[t] >= ntl[t]) continue;
+                    if (!it[t].valid()) continue;
+                    const int nkb = it[t].nkb(), skew = it[t].skew();
                     if (fresh[t]) {
-                        const int p = (int)((T0 + 2 * (k[t] / RPP) + t) / tiles_p);
+                        const int p = tp[t];
                         if (p != curp[t]) {
                             if (!mbar_test(&w0_full[t], w0loads[t] & 1)) continue;
                             ++w0loads[t];
@@ -460,11 +572,14 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     tc_commit(&acc0_full[t]);
                     ++l0cnt[t];
                     pos[t] += nk;
-                    if (pos[t] >= nkb) { pos[t] = 0; ++k[t]; fresh[t] = true; }
+                    if (pos[t] >= nkb) {
+                        pos[t] = 0; ++k[t]; fresh[t] = true;
+                        if (++d[t] == RPP) { d[t] = 0; it[t].next(T1, tiles_p, t, im.meta); tp[t] = it[t].valid() ? it[t].p(tiles_p) : -1; }
+                    }
                 }
             }
         }
-    } else if (warp >= 16) {
+    } else {
         // ================= layer-1 issuers: one thread per track (a track that waits for its epilogue
         // or its mid-stage does not hold the other one up; they drift at most NB W1 stages apart) ====
         // The whole warp runs the loop with warp-uniform state (so the compiler keeps it in uniform
@@ -474,7 +589,6 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
         {
             const int t = __shfl_sync(0xffffffffu, warp, 0) - 16;
             const bool leader = elect_one();
-            const int ntiles = t == 0 ? ntl[0] : ntl[1], first_blk = t * skew;
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * TM_TRACK + TM_ACC1);
             const uint64_t desc_hi = make_desc<64>(0) & 0xFFFFFFFF00000000ull;
             const uint32_t a_lo0 = (uint32_t)make_desc<64>(smem_u32(smem + C::A1_OFF + t * NS * A1_SLOT));
@@ -482,13 +596,18 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
             uint64_t* const a1f = a1_full + t * NS;
             uint64_t* const a1e = a1_empty + t * NS;
             uint32_t s = 0, bph = 0, slot = 0, sph = 0;
+            int kg = 0;                                      // tiles of this track so far (accumulator phase)
+            Seg sg;
+            for (bool live = seg_at(T0, T1, tiles_p, im.meta, RPP, sg); live; live = seg_at(sg.ta + sg.cnt, T1, tiles_p, im.meta, RPP, sg)) {
+            const int ntiles = t == 0 ? sg.n[0] : sg.n[1], first_blk = t * sg.skew, nkb = sg.nkb;
+            const uint32_t IDESC1 = idesc_f16(TILE_M, sg.ncol);
             int k = 0, pos = 0;
-            for (int nb = 0; nb < nblk; ++nb) {
+            for (int nb = 0; nb < sg.len; ++nb) {
                 mbar_wait(&b_full[s], bph);
                 if (nb < first_blk || k >= ntiles) {
                     if (leader) mbar_arrive(&b_empty[s]);   // this track does not use the block
                 } else {
-                    if (pos == 0) mbar_wait(&acc1_empty[t], ((uint32_t)k & 1) ^ 1);
+                    if (pos == 0) mbar_wait(&acc1_empty[t], ((uint32_t)kg & 1) ^ 1);
                     mbar_wait(&a1f[slot], sph);
                     tc_fence_after();
                     if (leader) {
@@ -504,18 +623,22 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     }
                     __syncwarp();
                     if (++slot == NS) { slot = 0; sph ^= 1; }
-                    if (++pos == nkb) { pos = 0; ++k; }
+                    if (++pos == nkb) { pos = 0; ++k; ++kg; }
                 }
                 if (++s == NB) { s = 0; bph ^= 1; }
             }
+            }
         }
+    }
     } else {
         // ================= worker teams: warps 0-7 epilogue (track 0, 1), warps 8-15 mid-stage =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         const int team = warp >> 2, t = team & 1;
         const int r = tid & 127, w = r >> 5;                  // w = TMEM lane quarter of this warp
         const uint32_t track_taddr = tmem_base + (uint32_t)(t * TM_TRACK);
-        const int nt = ntl[t];
-        if (nt == 0) goto done;
+        TrackIter cur;
+        cur.locate(T0, T1, tiles_p, t, im.meta);
+        if (!cur.valid()) goto done;
         if (team >= 2) {
             // ---------------- mid-stage (thread = row r): inputs -> A0, layer-0 accumulator -> A1 ----------------
             const uint32_t A0 = smem_u32(smem + C::A0_OFF + t * C::A0_BYTES);
@@ -526,9 +649,8 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
             uint32_t gate[MAX_NCH];            // sign bits of the primal pre-activations, one word per chunk (TAN)
 #pragma unroll
             for (int j = 0; j < MAX_NCH; ++j) gate[j] = 0;
-            auto fetch = [&](int ks) {         // item r of super-tile ks: particle p, item i -> global row i*P + p
-                const long long tau = T0 + 2 * ks + t;
-                const int p = (int)(tau / tiles_p), l = (int)(tau - (long long)p * tiles_p);
+            auto fetch = [&](const TrackIter& st) {   // item r of a super-tile: particle p, item i -> global row i*P + p
+                const int p = st.p(tiles_p), l = st.tau - p * tiles_p;
                 const int i = l * TILE_M + r;
                 vn = i < S;
 #pragma unroll
@@ -589,23 +711,27 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                 fence_async_smem();
                 mbar_arrive(&a0_full[t]);
             };
-            auto load_w0 = [&](int p) {
+            auto load_w0 = [&](int p, int nkb_p) {     // the chunks this particle uses: 32 hidden units = 2 K-blocks each
+                const uint32_t w0_bytes = (uint32_t)((nkb_p + 1) / 2) * C::W0_CHUNK;
                 mbar_expect_tx(&w0_full[t], w0_bytes);
                 bulk_g2s(smem + C::W0_OFF + t * C::W0_BYTES, im.W0img + (size_t)p * C::W0_BYTES, w0_bytes, &w0_full[t]);
             };
-            int curp = (int)((T0 + t) / tiles_p);
-            if (r == 0) load_w0(curp);
-            fetch(0);
+            int curp = cur.p(tiles_p);
+            if (r == 0) load_w0(curp, cur.nkb());
+            fetch(cur);
 #pragma unroll
             for (int k = 0; k < K0; ++k) inc[k] = inn[k];
             vc = vn;
             write_a0(0);
             uint32_t ci = 0, slot = 0, sph = 1;
-            const int kb0 = t * skew;
-            int ks = 0, d = 0;                 // super-tile and pass of the current tile
-            for (int k = 0; k < nt; ++k) {
+            TrackIter nxt = cur;
+            nxt.next(T1, tiles_p, t, im.meta);
+            int d = 0;                         // pass of the current tile inside its super-tile
+            while (cur.valid()) {
                 const bool last_pass = d == RPP - 1;
-                if (last_pass && k + 1 < nt) fetch(ks + 1);
+                const bool more = !last_pass || nxt.valid();        // another tile follows on this track
+                const int nkb = cur.nkb(), kb0 = t * cur.skew();
+                if (last_pass && nxt.valid()) fetch(nxt);
                 for (int pos = 0; pos < nkb;) {
                     int kb = kb0 + pos;
                     if (kb >= nkb) kb -= nkb;
@@ -618,11 +744,11 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     tc_wait_ld32(v);
                     tc_fence_before();
                     mbar_arrive(&acc0_empty[t]);
-                    if (pos + nk >= nkb && k + 1 < nt) {
+                    if (pos + nk >= nkb && more) {
                         // every layer-0 MMA of this tile has completed: A0 (and, between super-tiles, the W0 image) is free
                         if (last_pass) {
-                            const int pn = (int)((T0 + 2 * (ks + 1) + t) / tiles_p);
-                            if (pn != curp) { if (r == 0) load_w0(pn); curp = pn; }
+                            const int pn = nxt.p(tiles_p);
+                            if (pn != curp) { if (r == 0) load_w0(pn, nxt.nkb()); curp = pn; }
 #pragma unroll
                             for (int k2 = 0; k2 < K0; ++k2) inc[k2] = inn[k2];
                             vc = vn;
@@ -675,7 +801,7 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     }
                     pos += nk;
                 }
-                if (++d == RPP) { d = 0; ++ks; }
+                if (++d == RPP) { d = 0; cur = nxt; nxt.next(T1, tiles_p, t, im.meta); }
             }
         } else {
             // ---------------- epilogue: layer-1 accumulator -> ReLU -> output layer -> X', dX'/d(X,u) ----------------
@@ -688,13 +814,12 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
             const int q4 = lane & 3, rq = lane >> 2;
             int curp = -1;
             uint32_t w2loads = 0;
-            uint32_t gate[7];                  // sign bits of this thread's 208 primal pre-activations (TAN)
+            uint32_t gate[7];                  // sign bits of this thread's (up to 208) primal pre-activations (TAN)
 #pragma unroll
             for (int j = 0; j < 7; ++j) gate[j] = 0;
-            int ks = 0, d = 0;
-            for (int k = 0; k < nt; ++k) {
-                const long long tau = T0 + 2 * ks + t;
-                const int p = (int)(tau / tiles_p), l = (int)(tau - (long long)p * tiles_p);
+            int d = 0;
+            for (int k = 0; cur.valid(); ++k) {   // k = tiles of this track so far (accumulator phase)
+                const int p = cur.p(tiles_p), l = cur.tau - p * tiles_p, ncol = cur.ncol();
                 if (p != curp) {
                     named_bar_sync(1 + t, 128);      // every warp of the team is done with the old weights
                     if (r == 0) {
@@ -716,6 +841,17 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                         y[jr][o] = 0.f;
                         if constexpr (PK) y2[jr][o] = 0ull;
                     }
+                // the primal pass adds X to the network's output: request it now, the accumulator is not ready yet anyway
+                float xin[4][(D + 3) / 4];
+                if (!TAN || d == 0) {
+#pragma unroll
+                    for (int oo = 0; oo < (D + 3) / 4; ++oo)
+#pragma unroll
+                        for (int jr = 0; jr < 4; ++jr) {
+                            const int i = l * TILE_M + w * 32 + (jr >> 1) * 16 + (jr & 1) * 8 + rq, o = q4 + 4 * oo;
+                            xin[jr][oo] = (i < S && o < D) ? __ldg(a.X + ((size_t)i * P + p) * D + o) : 0.f;
+                        }
+                }
                 mbar_wait(&acc1_full[t], (uint32_t)k & 1);
                 tc_fence_after();
                 // half = 16 columns (two 8-column groups) of both row halves; consumes fragment buffer fb and
@@ -796,34 +932,42 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                     tc_ld_16x256b_x2(ta, fb[0]);
                     tc_ld_16x256b_x2(ta + (16u << 16), fb[1]);
                 };
-                auto push = [&](uint32_t word) {   // primal pass: push the new word; tangent passes: rotate (oldest = next)
+                // gate word of 32-column trip j: written by the primal pass, read by the tangent passes (register
+                // selects: the trip count depends on the particle, so the words cannot sit in a rotating queue)
+                auto gate_put = [&](int j, uint32_t word) {
 #pragma unroll
-                    for (int j = 6; j > 0; --j) gate[j] = gate[j - 1];
-                    gate[0] = word;
+                    for (int jj = 0; jj < 7; ++jj) if (jj == j) gate[jj] = word;
                 };
-                // 13 sixteen-column batches, two per trip of a ROLLED loop (a fully unrolled epilogue is 1 400 SASS
+                auto gate_get = [&](int j) -> uint32_t {
+                    uint32_t word = 0;
+#pragma unroll
+                    for (int jj = 0; jj < 7; ++jj) if (jj == j) word = gate[jj];
+                    return word;
+                };
+                // ncol / 16 sixteen-column batches, two per trip of a ROLLED loop (a fully unrolled epilogue is 1 400 SASS
                 // instructions: with five roles resident, instruction-cache misses were 26 % of its stall samples),
                 // software pipelined over two fragment buffers: the TMEM loads of the next batch are issued right
                 // after the wait for the current one (tcgen05.wait::ld waits for everything outstanding).
                 float fa[2][8], fb2[2][8];
+                const int cfull = ncol & ~31;               // columns covered by whole 32-column trips
                 issue(0, fa);
+                int j = 0;
 #pragma unroll 1
-                for (int c0 = 0; c0 < (TILE_N / 32) * 32; c0 += 32) {
-                    uint32_t word = (TAN && d != 0) ? gate[6] : 0u;
+                for (int c0 = 0; c0 < cfull; c0 += 32, ++j) {
+                    uint32_t word = (TAN && d != 0) ? gate_get(j) : 0u;
                     tc_wait_ld8(fa[0]); tc_wait_ld8(fa[1]);
                     issue(c0 + 16, fb2);
                     half(c0, fa, word, std::integral_constant<int, 0>(), std::integral_constant<int, 32>());
                     tc_wait_ld8(fb2[0]); tc_wait_ld8(fb2[1]);
-                    issue(c0 + 32, fa);
+                    if (c0 + 32 < ncol) issue(c0 + 32, fa);
                     half(c0 + 16, fb2, word, std::integral_constant<int, 16>(), std::integral_constant<int, 32>());
-                    if (TAN) push(word);
+                    if (TAN && d == 0) gate_put(j, word);
                 }
-                {
-                    static_assert(TILE_N % 32 == 16, "epilogue tail handles one 16-column batch");
-                    uint32_t word = (TAN && d != 0) ? gate[6] : 0u;
+                if (cfull < ncol) {                          // one more 16-column batch
+                    uint32_t word = (TAN && d != 0) ? gate_get(j) : 0u;
                     tc_wait_ld8(fa[0]); tc_wait_ld8(fa[1]);
-                    half((TILE_N / 32) * 32, fa, word, std::integral_constant<int, 0>(), std::integral_constant<int, 16>());
-                    if (TAN) push(word);
+                    half(cfull, fa, word, std::integral_constant<int, 0>(), std::integral_constant<int, 16>());
+                    if (TAN && d == 0) gate_put(j, word);
                 }
                 tc_fence_before();
                 mbar_arrive(&acc1_empty[t]);
@@ -849,13 +993,13 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
 #pragma unroll
                                 for (int o2 = 0; o2 < D; ++o2) if (o2 == o) yo = y[jr][o2];
                                 const size_t g = (size_t)i * P + p;
-                                if (!TAN || d == 0) a.Xn[g * D + o] = __ldg(a.X + g * D + o) + ((yo + bo) * sd + mn);
+                                if (!TAN || d == 0) a.Xn[g * D + o] = xin[jr][oo] + ((yo + bo) * sd + mn);
                                 else a.Jp[(g * D + o) * TD + (d - 1)] = ((d - 1) == o ? 1.f : 0.f) + yo * sd;
                             }
                         }
                     }
                 }
-                if (++d == RPP) { d = 0; ++ks; }
+                if (++d == RPP) { d = 0; cur.next(T1, tiles_p, t, im.meta); }
             }
         }
     }

@@ -533,6 +533,43 @@ def measure_e2e(name, rec, dtype, steps, dev, world, dist):
             "states_after_one_pass": dict(zip(("undefined", "accepted", "rejected", "not_pd", "max_reg", "converged"), states))}
 
 
+def measure_api_latency(dev, reps=20):
+    """Level-2 drop-in: the reference's module-level functions called the way its own `step()` calls
+    them, ONE problem at a time (pendulum, known dynamics, N = 100, 10 alphas) -- wall-clock milliseconds per call with
+    cached device buffers, including every host-side marshalling step and a device synchronisation."""
+    import pddp_b200 as P
+    from pddp_b200.controllers.ilqr import _control_law, _trajectory_cost, backward, forward
+    model, cost = P.examples.pendulum.PendulumDynamicsModel(0.1), P.examples.pendulum.PendulumCost()
+    enc = P.StateEncoding.IGNORE_UNCERTAINTY
+    g = torch.Generator().manual_seed(0)
+    z0 = (1e-2 * torch.randn(2, generator=g)).to(dev)
+    U = (0.1 * torch.randn(100, 1, generator=g)).to(dev)
+    alphas = (1.025 ** (-torch.arange(10.0) ** 2)).to(dev)
+    out = {}
+
+    def timed(name, fn):
+        fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        torch.cuda.synchronize(dev)
+        out[name + "_ms"] = (time.perf_counter() - t0) * 1e3 / reps
+        return r
+
+    lin = timed("forward", lambda: forward(z0, U, model, cost, enc))
+    k, K = timed("backward", lambda: backward(*lin, reg=1.0))
+    Zb, Ub = timed("control_law_10_alphas", lambda: _control_law(model, lin[0], U, k, K, alphas, enc))
+    timed("trajectory_cost", lambda: _trajectory_cost(cost, Zb, Ub, enc))
+    ctrl = P.controllers.iLQRController(None, model, cost)
+    timed("controller_fit_1_iteration", lambda: ctrl.fit(U, encoding=enc, n_iterations=1, z0=z0, quiet=True))
+    out["iteration_ms"] = out["forward_ms"] + out["backward_ms"] + out["control_law_10_alphas_ms"] + out["trajectory_cost_ms"]
+    out["trajectory_steps_per_s"] = 100 / (out["iteration_ms"] * 1e-3)
+    out["what"] = ("pendulum known dynamics, one problem, N = 100: forward / backward / _control_law / _trajectory_cost "
+                   "(reference signatures) and iLQRController.fit(n_iterations=1); launch-latency bound by construction")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -624,6 +661,12 @@ def main():
                 others.append({"workload": name, "dtype": dt, "error": "%s: %s" % (type(exc).__name__, exc)})
             torch.cuda.empty_cache()
 
+    api = None
+    if world == 1 and not args.no_others:
+        try:
+            api = measure_api_latency(dev)
+        except Exception as exc:
+            api = {"error": "%s: %s" % (type(exc).__name__, exc)}
     cpu = cpu_baseline_record(w) if rank == 0 and not args.no_cpu_baseline else None
     if rank == 0:
         line = {"metric": "trajectory-steps/s", "value": rec["value"], "unit": "trajectory-steps/s", "n_gpus": world,
@@ -631,7 +674,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": workload_config(args.workload, w), "clocks": rec["clocks"], "e2e": e2e,
                 "gpu_launches": rec["launches"], "roofline": roofline, "cpu_baseline": cpu,
-                "not_pd_problems": rec["not_pd"], "final_gather": gather, "strong": strong, "other_workloads": others}
+                "not_pd_problems": rec["not_pd"], "final_gather": gather, "strong": strong, "other_workloads": others,
+                "api_latency": api}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -233,7 +233,9 @@ __device__ __forceinline__ void store4(double* p, const double (&v)[4]) {
     *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
     *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
 }
-template <class T, int TEAM>
+// NZC > 0: encoded state size known at compile time (nz = 14: UT-Cholesky cartpole, nz = 42: full-covariance double
+// cartpole) -- the strip loops unroll and the index divisions fold away.
+template <class T, int TEAM, int NZC = 0>
 __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(const BackwardArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x % TEAM, warp = threadIdx.x / TEAM, wpb = blockDim.x / TEAM;
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(
     // rows padded to LD (a multiple of 4) so that a thread can own a 1 x 4 strip of an output row and
     // read its B operand with one 16-byte LDS per 4 FMAs (an element per thread needs 2 LDS per FMA,
     // and at nz = 42 the pass was bound by shared-memory loads)
-    const int nz = a.nz, nn = nz * nz, LD = (nz + 3) & ~3, NS4 = LD / 4, nl = nz * LD;
+    const int nz = NZC > 0 ? NZC : a.nz, nn = nz * nz, LD = (nz + 3) & ~3, NS4 = LD / 4, nl = nz * LD;
     const int per_team = backward_team_elems(nz);
     T* base = reinterpret_cast<T*>(smem_raw) + (size_t)warp * per_team;
     T *V = base, *Fz = base + nl, *W = base + 2 * nl;
@@ -363,17 +365,19 @@ cudaError_t backward_pass(const BackwardArgs<T>& a, int layout, cudaStream_t s) 
     const size_t per_team = (size_t)backward_team_elems(a.nz) * sizeof(T);
     if (a.nz >= 24) {                                   // a CTA per problem
         if (per_team > 227 * 1024) return cudaErrorInvalidValue;
-        cudaError_t e = cudaFuncSetAttribute(backward_warp_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_team);
+        auto kern = a.nz == 42 ? backward_warp_kernel<T, 256, 42> : backward_warp_kernel<T, 256, 0>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_team);
         if (e != cudaSuccess) return e;
-        backward_warp_kernel<T, 256><<<a.B, 256, per_team, s>>>(a);
+        kern<<<a.B, 256, per_team, s>>>(a);
         return cudaGetLastError();
     }
     int wpb = 4;
     while (wpb > 1 && per_team * wpb > 200 * 1024) wpb >>= 1;
     const size_t smem = per_team * wpb;
-    cudaError_t e = cudaFuncSetAttribute(backward_warp_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = a.nz == 14 ? backward_warp_kernel<T, 32, 14> : backward_warp_kernel<T, 32, 0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    backward_warp_kernel<T, 32><<<(a.B + wpb - 1) / wpb, wpb * 32, smem, s>>>(a);
+    kern<<<(a.B + wpb - 1) / wpb, wpb * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
 template cudaError_t backward_pass<float>(const BackwardArgs<float>&, int, cudaStream_t);

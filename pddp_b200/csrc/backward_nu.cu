@@ -29,9 +29,13 @@ template <int TEAM>
 __device__ __forceinline__ unsigned nu_team_mask() {
     return TEAM >= 32 ? 0xffffffffu : (((1u << (TEAM & 31)) - 1u) << ((threadIdx.x & 31) / TEAM * TEAM));
 }
+// Sub-warp teams synchronise with a FULL-warp barrier: it is also the point where the teams of a warp re-converge
+// after the data-dependent scalar part (Jacobi sweeps, box-QP iterations).  With per-team masks the teams stayed
+// diverged and the warp issued the matrix code once per team (17 k instructions per warp and time step).  Teams
+// that left the time loop (not positive definite) or the kernel are exited threads and do not take part.
 template <int TEAM>
 __device__ __forceinline__ void nu_team_sync() {
-    if (TEAM <= 32) __syncwarp(nu_team_mask<TEAM>()); else __syncthreads();
+    if (TEAM <= 32) __syncwarp(); else __syncthreads();
 }
 template <int TEAM>
 __device__ __forceinline__ bool nu_team_any(bool x) {
@@ -224,16 +228,22 @@ __device__ __forceinline__ int boxqp_n(int n, const T (&x0)[MNU], const T (&Q)[M
         T fc = qp_objective(n, Q, c, xc);
         while ((fc - old_f) / (step * sdotg) < armijo) {
             step *= step_dec;
-            bool same = true;
+            bool same = true, unchanged = true;
 #pragma unroll
             for (int i = 0; i < MNU; ++i) {
+                const T prev = xc[i];
                 xc[i] = i < n ? clampv(x[i] + step * search[i], lo[i], hi[i]) : T(0);
                 same = same && (xc[i] == x[i]);
+                unchanged = unchanged && (xc[i] == prev);
             }
             // the candidate has rounded back onto x and stays there for every smaller step: the reference
             // shrinks the step down to min_step and leaves x unchanged with result 2 (see boxqp1)
             if (same) { fc = old_f; result = 2; break; }
-            fc = qp_objective(n, Q, c, xc);
+            // a saturated Newton step (the direction is orders of magnitude longer than the box): every moving
+            // dimension sits on its bound for many consecutive step sizes, the candidate -- and so its objective --
+            // does not change, and only `step` in the Armijo ratio does.  Same iterations, same comparisons, without
+            // re-evaluating the objective (the loop was 23 % of the rendezvous backward pass's instructions).
+            if (!unchanged) fc = qp_objective(n, Q, c, xc);
             if (step < min_step) { result = 2; break; }
         }
 #pragma unroll
@@ -248,16 +258,25 @@ __host__ __device__ inline int backward_nu_elems(int nz, int nu) {
     const int LD = (nz + 3) & ~3;
     return 3 * nz * LD + 2 * LD + 4 * nu * LD + 32;
 }
+// stride between the teams of a CTA: == TEAM (mod 32) words, so that the 32 / TEAM teams of a warp, whose lanes read
+// TEAM consecutive words (or one broadcast word) at the same offset of their own region, hit 32 different banks
+// (an unpadded 368-word stride put the 8 teams of a warp on 2 bank groups: 73 % of the wavefronts were conflicts)
+__host__ __device__ inline int backward_nu_stride(int nz, int nu, int team) {
+    const int e = backward_nu_elems(nz, nu);
+    return team >= 32 ? e : ((e + 31) & ~31) + team;
+}
 
-template <class T, int TEAM>
+// NZC / NUC > 0: state / action sizes known at compile time (the loops unroll and the index divisions become shifts:
+// with run-time sizes the matrix phases of the rendezvous problem were 9.6 k instructions per warp and time step).
+template <class T, int TEAM, int NZC = 0, int NUC = 0>
 __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM) backward_nu_kernel(const BackwardArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x % TEAM, warp = threadIdx.x / TEAM, wpb = blockDim.x / TEAM;
     const int b = blockIdx.x * wpb + warp;
     if (b >= a.B) return;
     if (a.active && a.active[b] == 0) return;
-    const int nz = a.nz, nu = a.nu, nn = nz * nz, LD = (nz + 3) & ~3, nl = nz * LD;
-    T* base = reinterpret_cast<T*>(smem_raw) + (size_t)warp * backward_nu_elems(nz, nu);
+    const int nz = NZC > 0 ? NZC : a.nz, nu = NUC > 0 ? NUC : a.nu, nn = nz * nz, LD = (nz + 3) & ~3, nl = nz * LD;
+    T* base = reinterpret_cast<T*>(smem_raw) + (size_t)warp * backward_nu_stride(nz, nu, TEAM);
     T *V = base, *Fz = base + nl, *W = base + 2 * nl;
     T *v = base + 3 * nl, *Qz = v + LD;
     T *FuT = Qz + LD, *WuT = FuT + nu * LD, *Quz = WuT + nu * LD, *Kt = Quz + nu * LD;   // [nu][LD], row = control dim
@@ -340,44 +359,19 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM) backward_nu_kernel(co
             }
         }
         if (!finite) { ok = false; break; }                    // linalg.eig raises on NaN / Inf
-        // Eigen-clipping (ilqr.py:631-634) only changes Q_uu when it has a negative eigenvalue.  A Cholesky
-        // factorisation of Q_uu that succeeds proves there is none: then E diag(e + reg) E^T is Q_uu + reg I and
-        // (E / (e + reg)) E^T its inverse, and the Jacobi sweeps (most of this kernel's team-uniform scalar work)
-        // are skipped.  Indefinite Q_uu (early iterations, small mu) takes the eigen route.
-        const unsigned all_dims = (1u << nu) - 1u;
-        bool pd;
-        {
-            T Uc[MNU][MNU];
-            pd = masked_chol(Quu, all_dims, Uc);
-        }
-        if (!pd) {
-            jacobi_eig(nu, A, E, ev);
+        // (A Cholesky test for "Q_uu is already positive definite, skip the eigen-decomposition" was tried and
+        // measured SLOWER on the rendezvous workload: 40.6 vs 30.5 ms.  With R = 0.1 I the symmetric problem's Q_uu is
+        // diagonal up to rounding and the Jacobi loop exits before its first rotation, while the extra factorisation
+        // costs square roots, divisions and registers.)
+        jacobi_eig(nu, A, E, ev);
 #pragma unroll
-            for (int i = 0; i < MNU; ++i) {
-                if (ev[i] < T(0)) ev[i] = T(1e-12);            // ref: ilqr.py:633-634
-                ev[i] += reg;
-            }
+        for (int i = 0; i < MNU; ++i) {
+            if (ev[i] < T(0)) ev[i] = T(1e-12);                // ref: ilqr.py:633-634
+            ev[i] += reg;
         }
         T kt[MNU];
         T M[MNU][MNU];                                         // K = -M Q_uz   (M = regularised inverse on the free dims)
         if (!bounded) {
-            if (pd) {                                          // M = (Q_uu + reg I)^-1 by Cholesky
-                T Qr[MNU][MNU], Ur[MNU][MNU];
-#pragma unroll
-                for (int i = 0; i < MNU; ++i)
-#pragma unroll
-                    for (int j = 0; j < MNU; ++j) Qr[i][j] = Quu[i][j] + ((i == j && i < nu) ? reg : T(0));
-                masked_chol(Qr, all_dims, Ur);
-#pragma unroll
-                for (int j = 0; j < MNU; ++j) {
-                    T r[MNU], x[MNU];
-#pragma unroll
-                    for (int i = 0; i < MNU; ++i) r[i] = (i == j && j < nu) ? T(1) : T(0);
-                    chol_solve(Ur, r, x);
-#pragma unroll
-                    for (int i = 0; i < MNU; ++i) M[i][j] = (i < nu && j < nu) ? x[i] : T(0);
-                }
-            } else {
 #pragma unroll
                 for (int i = 0; i < MNU; ++i)
 #pragma unroll
@@ -388,7 +382,6 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM) backward_nu_kernel(co
                             if (m < nu) s += (E[i][m] / ev[m]) * E[j][m];
                         M[i][j] = (i < nu && j < nu) ? s : T(0);
                     }
-            }
 #pragma unroll
             for (int i = 0; i < MNU; ++i) {
                 T s = T(0);
@@ -407,13 +400,9 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM) backward_nu_kernel(co
 #pragma unroll
                 for (int j = 0; j < MNU; ++j) {
                     T s = T(0);
-                    if (pd) {
-                        s = (i < nu && j < nu) ? Quu[i][j] + (i == j ? reg : T(0)) : T(0);
-                    } else {
 #pragma unroll
-                        for (int m = 0; m < MNU; ++m)
-                            if (m < nu) s += (E[i][m] * ev[m]) * E[j][m];
-                    }
+                    for (int m = 0; m < MNU; ++m)
+                        if (m < nu) s += (E[i][m] * ev[m]) * E[j][m];
                     Qreg[i][j] = s;
                 }
             }
@@ -500,14 +489,16 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM) backward_nu_kernel(co
     if (lane == 0) a.status[b] = ok ? 0 : 1;
 }
 
-template <class T, int TEAM>
-static cudaError_t launch_nu_teams(const BackwardArgs<T>& a, size_t per_team, cudaStream_t s) {
+template <class T, int TEAM, int NZC = 0, int NUC = 0>
+static cudaError_t launch_nu_teams(const BackwardArgs<T>& a, size_t, cudaStream_t s) {
+    const size_t per_team = (size_t)backward_nu_stride(a.nz, a.nu, TEAM) * sizeof(T);
     int tpb = 128 / TEAM;                                   // teams (problems) per CTA
     while (tpb > 1 && per_team * tpb > 200 * 1024) tpb >>= 1;
     const size_t smem = per_team * tpb;
-    cudaError_t e = cudaFuncSetAttribute(backward_nu_kernel<T, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = backward_nu_kernel<T, TEAM, NZC, NUC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    backward_nu_kernel<T, TEAM><<<(a.B + tpb - 1) / tpb, tpb * TEAM, smem, s>>>(a);
+    kern<<<(a.B + tpb - 1) / tpb, tpb * TEAM, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -527,6 +518,7 @@ cudaError_t backward_pass_nu(const BackwardArgs<T>& a, cudaStream_t s) {
     static int forced_team = -1;
     if (forced_team < 0) { const char* e = getenv("PDDP_BACKWARD_NU_TEAM"); forced_team = e ? atoi(e) : 0; }
     const int team = forced_team ? forced_team : a.nz <= 8 ? 4 : a.nz <= 12 ? 8 : 32;
+    if (team == 4 && a.nz == 8 && a.nu == 4) return launch_nu_teams<T, 4, 8, 4>(a, per_team, s);    // rendezvous, IGNORE_UNCERTAINTY
     if (team == 4) return launch_nu_teams<T, 4>(a, per_team, s);
     if (team == 8) return launch_nu_teams<T, 8>(a, per_team, s);
     if (team == 16) return launch_nu_teams<T, 16>(a, per_team, s);

@@ -7,7 +7,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpddp_b200.so")
+LIB_PATH = os.environ.get("PDDP_B200_LIB") or os.path.join(_HERE, "lib", "libpddp_b200.so")   # (override: A/B experiment builds)
 
 F32, F64 = 0, 1
 PROBLEM_MAJOR, BATCH_INNER = 0, 1

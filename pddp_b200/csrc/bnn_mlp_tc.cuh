@@ -60,7 +60,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the
 // hint expires.  Without a hint the default window is ~50 cycles: the waiting roles re-polled 60 M
 // times per launch, and the kernel runs into the board's power cap.
+#ifdef PDDP_EXP_SUSPEND_NS
+constexpr uint32_t MBAR_SUSPEND_NS = PDDP_EXP_SUSPEND_NS;
+#else
 constexpr uint32_t MBAR_SUSPEND_NS = 20000;
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -615,8 +619,10 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                         const uint64_t bd = desc_hi | (uint64_t)(b_lo0 + s * (B_STAGE >> 4));
                         // one UMMA K-step = 32 B of a row = 16 fp16: [x0 | x1] halves are +2 apart in the >>4 address field
                         tc_mma_f16(d_tmem, ad, bd, IDESC1, pos != 0);     // a0 * b0
+#ifndef PDDP_EXP_ONE_PASS            // (timing experiment: a single FP16 pass)
                         tc_mma_f16(d_tmem, ad, bd + 2, IDESC1, 1);        // a0 * b1
                         tc_mma_f16(d_tmem, ad + 2, bd, IDESC1, 1);        // a1 * b0
+#endif
                         tc_commit(&a1e[slot]);
                         tc_commit(&b_empty[s]);
                         if (pos == nkb - 1) tc_commit(&acc1_full[t]);
@@ -786,8 +792,12 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                             for (int e = 0; e < 8; ++e) {
                                 const float v0 = v[16 * h + 2 * e], v1 = v[16 * h + 2 * e + 1];
                                 a0[e] = pack_f16(v0, v1);
+#ifdef PDDP_EXP_MID_CHEAP            // timing experiment only (wrong results): no lo part
+                                a1[e] = 0u;
+#else
                                 const float2 back = unpack_f16(a0[e]);
                                 a1[e] = pack_f16(v0 - back.x, v1 - back.y);
+#endif
                             }
 #pragma unroll
                             for (int c = 0; c < 2; ++c) {     // 16-byte chunks 0,1 = a0[0..7], a0[8..15]; 2,3 = a1
@@ -819,7 +829,11 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
             for (int j = 0; j < 7; ++j) gate[j] = 0;
             int d = 0;
             for (int k = 0; cur.valid(); ++k) {   // k = tiles of this track so far (accumulator phase)
+#ifdef PDDP_EXP_EPI_SHORT            // timing experiment only (wrong results): the epilogue drains 16 columns
+                const int p = cur.p(tiles_p), l = cur.tau - p * tiles_p, ncol = 16;
+#else
                 const int p = cur.p(tiles_p), l = cur.tau - p * tiles_p, ncol = cur.ncol();
+#endif
                 if (p != curp) {
                     named_bar_sync(1 + t, 128);      // every warp of the team is done with the old weights
                     if (r == 0) {
@@ -993,6 +1007,9 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
 #pragma unroll
                                 for (int o2 = 0; o2 < D; ++o2) if (o2 == o) yo = y[jr][o2];
                                 const size_t g = (size_t)i * P + p;
+#ifdef PDDP_EXP_NO_STORE             // timing experiment only: one store per tile
+                                if (i != 0) continue;
+#endif
                                 if (!TAN || d == 0) a.Xn[g * D + o] = xin[jr][oo] + ((yo + bo) * sd + mn);
                                 else a.Jp[(g * D + o) * TD + (d - 1)] = ((d - 1) == o ? 1.f : 0.f) + yo * sd;
                             }

@@ -245,8 +245,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 template <int K0P, int DP>
 struct Cfg {
+#if defined(PDDP_EXP_NB) && defined(PDDP_EXP_NS)
+    static constexpr int NB = PDDP_EXP_NB, NS = PDDP_EXP_NS;
+#else
     static constexpr int NB = K0P == 8 ? 5 : 4;    // W1 K-block stages
     static constexpr int NS = K0P == 8 ? 6 : 4;    // layer-1 A-operand slots per track
+#endif
     static constexpr int ROWB0 = K0P * 4;          // layer-0 operand row [x0 (K0P fp16) | x1 (K0P fp16)]: SWIZZLE_32B / 64B
     static constexpr int A0_BYTES = TILE_M * ROWB0;
     static constexpr int W0_CHUNK_PART = N0 * ROWB0, W0_CHUNK = 2 * W0_CHUNK_PART, W0_BYTES = MAX_NCH * W0_CHUNK;

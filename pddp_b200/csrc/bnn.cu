@@ -835,3 +835,11 @@ extern "C" int pddp_rollout_bnn(const pddp_shape* s, const pddp_bnn* n, const pd
     cudaError_t e = s->dtype == PDDP_F32 ? rollout_bnn_t<float>(c) : rollout_bnn_t<double>(c);
     return pddp_capi_cuda(e, "pddp_rollout_bnn");
 }
+
+#ifdef PDDP_EXP_TRACE
+// (timeline experiment) copies CTA 0's trace of the last tcgen05 MLP launch to the host
+extern "C" int pddp_debug_trace(long long* dst, size_t n) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(dst, pddp::tc::g_trace, n * sizeof(long long));
+}
+#endif

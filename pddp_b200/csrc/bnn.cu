@@ -13,14 +13,15 @@
 // data supplied by the caller, so there is no RNG on this path.
 #include "../../include/pddp_b200.h"
 #include "bnn_common.cuh"
-#include "bnn_mlp_simt.cuh"
-#include "bnn_mlp_tc.cuh"
+#include "bnn_mlp_iface.h"
 #include "kernels.h"
 #include "profile.h"
 #include <stdio.h>
 #include <stdlib.h>
 
 namespace pddp {
+
+#define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return e__; } while (0)
 
 // ------------------------------------------------------------------------------------------
 // weight prep: torch [out,in] -> [in,out] copies in the workspace (coalesced over outputs)
@@ -69,6 +70,12 @@ __global__ void bnn_init_particles_kernel(const T* z, Layout lz, int t, int zdiv
 // ------------------------------------------------------------------------------------------
 // linearise: moment matching + Jacobian of one step, one warp per problem
 // ------------------------------------------------------------------------------------------
+// shared-memory elements of ONE problem in bnn_moment_lin_kernel (arrays padded to 16 bytes)
+template <int D, int WPP>
+__host__ __device__ constexpr int moment_lin_smem_elems(int P) {
+    return 2 * ((P * D + 3) & ~3) + ((P * (D + 1) * D + 3) & ~3) + (WPP > 1 ? WPP * 32 : 0);
+}
+
 template <class T>
 struct MomentLinArgs {
     int B, N, t, P;
@@ -78,19 +85,72 @@ struct MomentLinArgs {
     Layout lZ, lFz, lFu;
 };
 
-template <class T, int GEO, int ENC>
-__global__ void __launch_bounds__(128) bnn_moment_lin_kernel(const MomentLinArgs<T> a) {
+// N consecutive elements with the widest vector access the alignment allows: 16 bytes when a row (N elements) is a
+// multiple of 16 bytes, else 8 bytes (every array here starts 16-byte aligned and N is even), else scalar.
+template <int N, class T>
+__device__ __forceinline__ void load_row(const T* p, T* out) {
+    constexpr int ROWB = N * (int)sizeof(T);
+    if constexpr (ROWB % 16 == 0) {
+#pragma unroll
+        for (int i = 0; i < ROWB / 16; ++i) reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(p)[i];
+    } else if constexpr (ROWB % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < ROWB / 8; ++i) reinterpret_cast<float2*>(out)[i] = reinterpret_cast<const float2*>(p)[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = p[i];
+    }
+}
+
+// One problem = a TEAM of WPP warps (4 warps per CTA).  Phase 1, lanes = particles: eps = (X - m) U^-1, X' and the
+// per-particle Jacobian [dX'/dX | dX'/du] staged in shared memory TRANSPOSED (row c = derivative w.r.t. input c, so
+// one direction reads one contiguous row), mean and covariance by warp shuffles (+ a shared-memory step across the
+// team's warps).  Phase 2, lanes = (input direction j, 1 of SPLIT particle subsets): the tangent of every particle
+// along j, its mean and its second moment with the centred particles, then the encode differential.
+// For the sparse encodings (everything but FULL_COVARIANCE_MATRIX) a direction moves ONE component of the input
+// particle: dX_p = s_p e_c with s_p = 1 (mean directions), eps_p[r] dU_rr/dz_j (factor directions) -- or it is the
+// control direction -- so dX'_p is one scaled row of the staged Jacobian instead of a dense D x D product
+// (the dense form added exact zeros: same values).
+template <class T, int GEO, int ENC, int WPP>
+__global__ void __launch_bounds__(128, (sizeof(T) == 4 && WPP == 1 && Geo<GEO>::D <= 4) ? 8 : (sizeof(T) == 4 ? 4 : 1)) bnn_moment_lin_kernel(const MomentLinArgs<T> a) {
     typedef Geo<GEO> G;
-    constexpr int D = G::D, NU = G::NU, NZ = enc_size(D, ENC), TD = D + NU, NT = D * (D + 1) / 2;
+    constexpr int D = G::D, NU = G::NU, NZ = enc_size(D, ENC), NT = D * (D + 1) / 2, TL = WPP * 32, PPB = 4 / WPP;
+    static_assert(NU == 1, "BNN geometries are the action_size-1 problems");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int b = blockIdx.x * wpb + warp;
-    if (b >= a.B) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = warp / WPP, wq = warp % WPP, tl = wq * 32 + lane;
+    const int b = blockIdx.x * PPB + slot;
+    if (b >= a.B) return;                                 // (the whole team leaves together)
     if (a.active && a.active[b] != 1) return;
     const int P = a.P, t = a.t;
-    const int per = P * (3 * D + D * D);
-    T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)warp * per;
-    T *s_eps = sm, *s_xc = sm + P * D, *s_H = sm + 2 * P * D, *s_G = sm + 3 * P * D;   // eps, X'-M', dX'/du, dX'/dX
+    const int PD4 = (P * D + 3) & ~3, PG4 = (P * (D + 1) * D + 3) & ~3;
+    T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)slot * moment_lin_smem_elems<D, WPP>(P);
+    T *s_eps = sm, *s_xc = sm + PD4, *s_G = sm + 2 * PD4, *s_red = s_G + PG4;   // eps, X'-M', [dX'/dX | dX'/du]^T, scratch
+    auto team_sync = [&]() {
+        if constexpr (WPP == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(TL) : "memory");
+    };
+    // sums of N <= 32 per-lane values over the team
+    auto team_sum = [&](auto& v) {
+        constexpr int N = (int)(sizeof(v) / sizeof(v[0]));
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+        if constexpr (WPP > 1) {
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) s_red[wq * 32 + i] = v[i];
+            }
+            team_sync();
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                T acc = s_red[i];
+#pragma unroll
+                for (int w2 = 1; w2 < WPP; ++w2) acc += s_red[w2 * 32 + i];
+                v[i] = acc;
+            }
+            team_sync();
+        }
+    };
 
     T z[NZ];
 #pragma unroll
@@ -102,32 +162,35 @@ __global__ void __launch_bounds__(128) bnn_moment_lin_kernel(const MomentLinArgs
     T msum[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) msum[d] = T(0);
-    for (int p = lane; p < P; p += 32) {
+    for (int p = tl; p < P; p += TL) {
         const size_t g = (size_t)b * P + p;
+        alignas(16) T x[D], xn[D], jac[D * (D + 1)];
         T delta[D], eps[D];
+        load_row<D, T>(a.X + g * D, x);
+        load_row<D, T>(a.Xn + g * D, xn);
+        load_row<D * (D + 1), T>(a.Jp + g * D * (D + 1), jac);
 #pragma unroll
-        for (int d = 0; d < D; ++d) delta[d] = a.X[g * D + d] - z[d];
+        for (int d = 0; d < D; ++d) delta[d] = x[d] - z[d];
         solve_right_upper<D, T>(U, delta, eps);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             s_eps[p * D + d] = eps[d];
-            T xn = a.Xn[g * D + d];
-            s_xc[p * D + d] = xn;
-            msum[d] += xn;
+            s_xc[p * D + d] = xn[d];
+            msum[d] += xn[d];
 #pragma unroll
-            for (int c = 0; c < TD; ++c) {
-                T j = a.Jp[(g * D + d) * TD + c];
-                if (c < D) s_G[(p * D + d) * D + c] = j; else s_H[p * D + d] = j;
-            }
+            for (int c = 0; c <= D; ++c) s_G[(p * (D + 1) + c) * D + d] = jac[d * (D + 1) + c];
         }
     }
     T M[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) M[d] = warp_sum(msum[d]) / T(P);
+    for (int d = 0; d < D; ++d) M[d] = msum[d];
+    team_sum(M);
+#pragma unroll
+    for (int d = 0; d < D; ++d) M[d] /= T(P);
     T csum[NT];
 #pragma unroll
     for (int i = 0; i < NT; ++i) csum[i] = T(0);
-    for (int p = lane; p < P; p += 32) {
+    for (int p = tl; p < P; p += TL) {
         T xc[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) { xc[d] = s_xc[p * D + d] - M[d]; s_xc[p * D + d] = xc[d]; }
@@ -136,47 +199,50 @@ __global__ void __launch_bounds__(128) bnn_moment_lin_kernel(const MomentLinArgs
 #pragma unroll
             for (int c = r; c < D; ++c) csum[tri<D>(r, c)] += xc[r] * xc[c];
     }
+    team_sum(csum);
     T Cov[D][D];
 #pragma unroll
     for (int r = 0; r < D; ++r)
 #pragma unroll
         for (int c = r; c < D; ++c) {
-            T v = warp_sum(csum[tri<D>(r, c)]) / T(P - 1);    // ref: utils/particles.py:136-149
+            T v = csum[tri<D>(r, c)] / T(P - 1);    // ref: utils/particles.py:136-149
             Cov[r][c] = v;
             Cov[c][r] = v;
         }
-    __syncwarp();
+    team_sync();
     T zn[NZ], Un[D][D];
     ok = encode_moments<D, ENC, T>(M, Cov, zn, Un) && ok;
 #pragma unroll
     for (int e = 0; e < NZ; ++e)
-        if ((e & 31) == lane) a.Z[a.lZ.at(b, t + 1, e)] = zn[e];
-    if (lane == 0 && !ok && a.status) a.status[b] |= 2;
+        if ((e % TL) == tl) a.Z[a.lZ.at(b, t + 1, e)] = zn[e];
+    if (tl == 0 && !ok && a.status) a.status[b] |= 2;
 
-    // SPLIT lanes per input direction j in [z (NZ), u (NU)], each taking every SPLIT-th particle (with
-    // one lane per direction only NZ + NU of the 32 lanes work: 15 for the UT-Cholesky cartpole)
-    constexpr int NJ = NZ + NU, SPLIT = NJ * 4 <= 32 ? 4 : (NJ * 2 <= 32 ? 2 : 1), JPW = 32 / SPLIT;
+    // SPLIT lanes per input direction j in [z (NZ), u (NU)], each taking every SPLIT-th particle
+    constexpr int NJ = NZ + NU;
+    constexpr int SPLIT = NJ * 8 <= TL ? 8 : NJ * 4 <= TL ? 4 : (NJ * 2 <= TL ? 2 : 1), JPW = 32 / SPLIT, JPT = WPP * JPW;
     const int sub = lane % SPLIT;
-    for (int j0 = 0; j0 < NJ; j0 += JPW) {
-        const int jraw = j0 + lane / SPLIT;
+    for (int j0 = 0; j0 < NJ; j0 += JPT) {
+        const int jraw = j0 + wq * JPW + lane / SPLIT;
         const bool jvalid = jraw < NJ;
         if (SPLIT == 1 && !jvalid) continue;              // no shuffles below in that case
         const int j = jvalid ? jraw : NJ - 1;
-        T dm[D], dUd[D][D], du = T(0);
+        T dM[D], S2[D][D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) dm[d] = (j == d) ? T(1) : T(0);
+        for (int r = 0; r < D; ++r) {
+            dM[r] = T(0);
 #pragma unroll
-        for (int r = 0; r < D; ++r)
+            for (int c = 0; c < D; ++c) S2[r][c] = T(0);
+        }
+        if constexpr (ENC == ENC_FULL) {
+            T dm[D], dUd[D][D], du = T(0);
 #pragma unroll
-            for (int c = 0; c < D; ++c) dUd[r][c] = T(0);
-        if (j >= NZ) du = T(1);
-        else if (j >= D) {
-            if (ENC == ENC_UT) {
+            for (int d = 0; d < D; ++d) dm[d] = (j == d) ? T(1) : T(0);
 #pragma unroll
-                for (int r = 0; r < D; ++r)
+            for (int r = 0; r < D; ++r)
 #pragma unroll
-                    for (int c = r; c < D; ++c) dUd[r][c] = (j - D == tri<D>(r, c)) ? T(1) : T(0);
-            } else if (ENC == ENC_FULL) {
+                for (int c = 0; c < D; ++c) dUd[r][c] = T(0);
+            if (j >= NZ) du = T(1);
+            else if (j >= D) {
                 // symmetrised direction (E_ab + E_ba)/2 through the Cholesky differential
                 T S[D][D];
                 const int ja = (j - D) / D, jb = (j - D) - ja * D;
@@ -186,45 +252,64 @@ __global__ void __launch_bounds__(128) bnn_moment_lin_kernel(const MomentLinArgs
                     for (int c = 0; c < D; ++c)
                         S[r][c] = ((r == ja && c == jb) ? T(0.5) : T(0)) + ((r == jb && c == ja) ? T(0.5) : T(0));
                 chol_upper_diff<D, T>(U, S, dUd);
-            } else if (ENC == ENC_VAR) {         // U = diag(sqrt(v)): dU_aa / dv_a = 1 / (2 U_aa)
-#pragma unroll
-                for (int r = 0; r < D; ++r) dUd[r][r] = (j - D == r) ? T(0.5) / U[r][r] : T(0);
-            } else if (ENC == ENC_STD) {
-#pragma unroll
-                for (int r = 0; r < D; ++r) dUd[r][r] = (j - D == r) ? T(1) : T(0);
             }
-        }
-        T dM[D], S2[D][D];
+            for (int p = sub; p < P; p += SPLIT) {
+                alignas(16) T eps[D], xc[D], g[D + 1][D];
+                T dx[D];
+                load_row<D, T>(s_eps + p * D, eps);
+                load_row<D, T>(s_xc + p * D, xc);
+                load_row<(D + 1) * D, T>(s_G + p * (D + 1) * D, &g[0][0]);
 #pragma unroll
-        for (int r = 0; r < D; ++r) {
-            dM[r] = T(0);
+                for (int c = 0; c < D; ++c) {
+                    T v = dm[c];
 #pragma unroll
-            for (int c = 0; c < D; ++c) S2[r][c] = T(0);
-        }
-        for (int p = sub; p < P; p += SPLIT) {
-            T dx[D], dxn[D];
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                T v = dm[c];
-                if (ENC != ENC_IGNORE) {
-#pragma unroll
-                    for (int r = 0; r <= c; ++r) v += s_eps[p * D + r] * dUd[r][c];
+                    for (int r = 0; r <= c; ++r) v += eps[r] * dUd[r][c];
+                    dx[c] = v;
                 }
-                dx[c] = v;
+#pragma unroll
+                for (int r = 0; r < D; ++r) {
+                    T v = g[D][r] * du;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) v += g[c][r] * dx[c];
+                    dM[r] += v;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) S2[r][c] += v * xc[c];
+                }
             }
+        } else {
+            // row of the staged Jacobian this direction reads, the eps component that scales it (-1: none) and
+            // the constant factor dU_rr/dz_j
+            int row = j < D ? j : D, er = -1;
+            T wgt = T(1);
+            if (j >= D && j < NZ) {
+                if (ENC == ENC_UT) {
 #pragma unroll
-            for (int r = 0; r < D; ++r) {
-                T v = s_H[p * D + r] * du;
+                    for (int r = 0; r < D; ++r)
 #pragma unroll
-                for (int c = 0; c < D; ++c) v += s_G[(p * D + r) * D + c] * dx[c];
-                dxn[r] = v;
-                dM[r] += v;
+                        for (int c = r; c < D; ++c) if (j - D == tri<D>(r, c)) { er = r; row = c; }
+                } else {                                  // VAR: U = diag(sqrt(v)), dU_aa/dv_a = 1 / (2 U_aa); STD: U = diag(s)
+                    er = row = j - D;
+                    if (ENC == ENC_VAR) {
+#pragma unroll
+                        for (int r = 0; r < D; ++r) if (r == er) wgt = T(0.5) / U[r][r];
+                    }
+                }
             }
-            if (ENC != ENC_IGNORE) {
+            for (int p = sub; p < P; p += SPLIT) {
+                alignas(16) T xc[D], g[D];
+                load_row<D, T>(s_G + (p * (D + 1) + row) * D, g);
+                T sc = T(1);
+                if (ENC != ENC_IGNORE && er >= 0) sc = s_eps[p * D + er] * wgt;
+                if (ENC != ENC_IGNORE) load_row<D, T>(s_xc + p * D, xc);
 #pragma unroll
-                for (int r = 0; r < D; ++r)
+                for (int r = 0; r < D; ++r) {
+                    const T v = er >= 0 ? g[r] * sc : g[r];
+                    dM[r] += v;
+                    if (ENC != ENC_IGNORE) {
 #pragma unroll
-                    for (int c = 0; c < D; ++c) S2[r][c] += dxn[r] * s_xc[p * D + c];
+                        for (int c = 0; c < D; ++c) S2[r][c] += v * xc[c];
+                    }
+                }
             }
         }
         if (SPLIT > 1) {
@@ -304,31 +389,65 @@ struct RollStepArgs {
     Layout lZ, lU, lk, lK;
 };
 
-// CTA = 256 threads = 32 (problem, alpha) pairs.  Phase A: 8 lanes per pair stream its P particles
-// (coalesced 128-byte rows of the [pair][particle][D] array) and reduce mean and covariance with
-// three xor-shuffles; phase B: warp 0, one lane per pair, does the encode (Cholesky), control law and
-// moment-matched cost.  (One thread per pair issued 2 x P strided 4-byte loads per sector and ran at
-// 9 % issue utilisation; a warp per pair left 31 lanes idle through phase B.)
-template <class T, int GEO, int ENC>
+// CTA = 256 threads = 256 / LPP (problem, alpha) pairs.  The particles of the CTA's pairs are ONE contiguous block of
+// the [pair][particle][D] array: a single cp.async.bulk stages it in shared memory while the threads that will finish
+// the pairs already fetch their rows of the nominal trajectory and the gains (Z[t+1], K[t+1], k, U: ilqr.py:701-719).
+// Phase A: LPP (8 or 4) lanes per pair reduce mean and covariance from shared memory (xor-shuffles); phase B: the
+// first 256 / LPP threads, one per pair, do the encode (Cholesky), control law and moment-matched cost.
+// (History: one thread per pair issued 2 x P strided 4-byte loads per sector and ran at 9 % issue utilisation; 8 lanes
+// per pair reading global memory directly spent the launch in 2 x P / LPP dependent round trips to L2: 28 us.)
+template <class T, int GEO, int ENC, int LPP>
 __global__ void __launch_bounds__(256) bnn_roll_step_kernel(const RollStepArgs<T> a) {
     typedef Geo<GEO> G;
-    constexpr int D = G::D, NZ = enc_size(D, ENC), NT = D * (D + 1) / 2, LPP = 8, PPC = 32;
+    constexpr int D = G::D, NZ = enc_size(D, ENC), NT = D * (D + 1) / 2, PPC = 256 / LPP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ T s_mom[PPC][D + NT];
+    __shared__ __align__(8) uint64_t s_bar;
+    T* s_X = reinterpret_cast<T*>(smem_raw);                 // [PPC][P][D]
     const int tid = threadIdx.x;
     const long long S = (long long)a.B * a.A;
     const int P = a.P, t1 = a.t + 1;
+    const long long s0 = (long long)blockIdx.x * PPC;
     if (a.t >= 0) {
+        if (tid == 0) bulk_mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const long long np = S - s0 < PPC ? S - s0 : PPC;
+            const uint32_t bytes = (uint32_t)((np * P * D * sizeof(T) + 15) & ~15ull);   // (the workspace arrays are padded)
+            bulk_load(s_X, a.Xn + (size_t)s0 * P * D, bytes, &s_bar);
+        }
+    }
+    // the finishing thread of a pair: rows it needs, requested before anything waits
+    const long long sB = s0 + tid;
+    const bool fin = tid < PPC && sB < S;
+    int b = 0, al = 0;
+    bool run = false;
+    T zref[NZ], Krow[NZ], kk = T(0), uu = T(0), alpha = T(0), Jprev = T(0);
+    if (fin) {
+        b = (int)(sB / a.A); al = (int)(sB - (long long)b * a.A);
+        run = !((a.active && a.active[b] == 0) || (a.bw_status && a.bw_status[b] != 0));
+        if (run && t1 < a.N) {
+#pragma unroll
+            for (int e = 0; e < NZ; ++e) { zref[e] = a.Z[a.lZ.at(b, t1, e)]; Krow[e] = a.K[a.lK.at(b, t1, e)]; }
+            kk = a.k[a.lk.at(b, t1, 0)]; uu = a.U[a.lU.at(b, t1, 0)]; alpha = a.alphas[al];
+        }
+        if (run && a.t >= 0) Jprev = a.J[sB];
+    }
+    if (a.t >= 0) {
+        bulk_mbar_wait(&s_bar, 0);
         const int pr = tid / LPP, sub = tid % LPP;
-        const long long s = (long long)blockIdx.x * PPC + pr;
-        const bool live = s < S;
-        const T* X = a.Xn + (size_t)(live ? s : 0) * P * D;
+        const bool live = s0 + pr < S;
+        const T* X = s_X + (size_t)pr * P * D;
         T M[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) M[d] = T(0);
         if (live)
-            for (int p = sub; p < P; p += LPP)
+            for (int p = sub; p < P; p += LPP) {
+                alignas(16) T x[D];
+                load_row<D, T>(X + p * D, x);
 #pragma unroll
-                for (int d = 0; d < D; ++d) M[d] += X[p * D + d];
+                for (int d = 0; d < D; ++d) M[d] += x[d];
+            }
 #pragma unroll
         for (int d = 0; d < D; ++d) {
 #pragma unroll
@@ -340,9 +459,11 @@ __global__ void __launch_bounds__(256) bnn_roll_step_kernel(const RollStepArgs<T
         for (int i = 0; i < NT; ++i) cs[i] = T(0);
         if (live)
             for (int p = sub; p < P; p += LPP) {
+                alignas(16) T x[D];
                 T xc[D];
+                load_row<D, T>(X + p * D, x);
 #pragma unroll
-                for (int d = 0; d < D; ++d) xc[d] = X[p * D + d] - M[d];
+                for (int d = 0; d < D; ++d) xc[d] = x[d] - M[d];
 #pragma unroll
                 for (int r = 0; r < D; ++r)
 #pragma unroll
@@ -361,11 +482,8 @@ __global__ void __launch_bounds__(256) bnn_roll_step_kernel(const RollStepArgs<T
         }
     }
     __syncthreads();
-    if (tid >= PPC) return;
-    const long long s = (long long)blockIdx.x * PPC + tid;
-    if (s >= S) return;
-    const int b = (int)(s / a.A), al = (int)(s - (long long)b * a.A);
-    if ((a.active && a.active[b] == 0) || (a.bw_status && a.bw_status[b] != 0)) return;
+    if (!fin || !run) return;
+    const long long s = sB;
     T zn[NZ];
     bool ok = true;
     if (a.t < 0) {
@@ -388,12 +506,12 @@ __global__ void __launch_bounds__(256) bnn_roll_step_kernel(const RollStepArgs<T
 #pragma unroll
     for (int e = 0; e < NZ; ++e) zrow[e] = zn[e];
     if (!ok && a.status) atomicOr(&a.status[b], 2);
-    T J = a.t < 0 ? T(0) : a.J[s];
+    T J = Jprev;
     if (t1 < a.N) {                                       // control law (ref: ilqr.py:701-719)
-        T du = a.alphas[al] * a.k[a.lk.at(b, t1, 0)];
+        T du = alpha * kk;
 #pragma unroll
-        for (int e = 0; e < NZ; ++e) du += (zn[e] - a.Z[a.lZ.at(b, t1, e)]) * a.K[a.lK.at(b, t1, e)];
-        T u = a.U[a.lU.at(b, t1, 0)] + du;
+        for (int e = 0; e < NZ; ++e) du += (zn[e] - zref[e]) * Krow[e];
+        T u = uu + du;
         if (a.u_min && a.u_max) u = clampv(u, a.u_min[0], a.u_max[0]);
         a.ucur[s] = u;
         a.Uall[(size_t)s * a.N + t1] = u;
@@ -433,17 +551,6 @@ __global__ void bnn_roll_select_kernel(int B, int N, int A, int nz, const T* J, 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
-static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
-    return g_num_sms;
-}
-
 template <class T>
 struct Workspace {
     T *W0T, *W1T, *W2T, *m0T, *m1T, *Xa, *Xb, *Jp, *ucur, *J, *Zall, *Uall;
@@ -471,13 +578,13 @@ static Workspace<T> carve(void* base, const pddp_shape* s, const pddp_bnn* n, in
     w.J = take(S);
     w.Zall = take(S * (s->N + 1) * s->nz);
     w.Uall = take(S * s->N);
-    w.im.W1img = reinterpret_cast<unsigned char*>(take(P * tc::W1_PSTRIDE / sizeof(T)));        // per-particle (compacted) images
-    w.im.W0img = reinterpret_cast<unsigned char*>(take(P * (size_t)tc::Cfg<16, 8>::W0_BYTES / sizeof(T)));
-    w.im.W2p = reinterpret_cast<float*>(take(P * (size_t)tc::TILE_N * 8 * sizeof(float) / sizeof(T)));
+    w.im.W1img = reinterpret_cast<unsigned char*>(take(P * tc::IMG_W1_PSTRIDE / sizeof(T)));        // per-particle (compacted) images
+    w.im.W0img = reinterpret_cast<unsigned char*>(take(P * tc::IMG_W0_PSTRIDE / sizeof(T)));
+    w.im.W2p = reinterpret_cast<float*>(take(P * (size_t)tc::IMG_TILE_N * 8 * sizeof(float) / sizeof(T)));
     w.im.scale = reinterpret_cast<float*>(take(256 / sizeof(T)));
-    w.im.meta = reinterpret_cast<int*>(take(P * (size_t)tc::META * sizeof(int) / sizeof(T) + 1));
-    w.im.idx0 = reinterpret_cast<int*>(take(P * (size_t)tc::TILE_N * sizeof(int) / sizeof(T)));
-    w.im.idx1 = reinterpret_cast<int*>(take(P * (size_t)tc::TILE_N * sizeof(int) / sizeof(T)));
+    w.im.meta = reinterpret_cast<int*>(take(P * (size_t)tc::IMG_META * sizeof(int) / sizeof(T) + 1));
+    w.im.idx0 = reinterpret_cast<int*>(take(P * (size_t)tc::IMG_TILE_N * sizeof(int) / sizeof(T)));
+    w.im.idx1 = reinterpret_cast<int*>(take(P * (size_t)tc::IMG_TILE_N * sizeof(int) / sizeof(T)));
     w.bytes = off;
     return w;
 }
@@ -496,16 +603,6 @@ static BnnNet<T> make_net(const pddp_bnn* n, const Workspace<T>& w) {
     return r;
 }
 
-// The tcgen05 kernel covers fp32 with hidden widths in (64, 207] x (64, 208] (H0 + 1 <= 208: the
-// bias column); everything else (fp64, small nets) runs the SIMT kernel.  PDDP_FORCE_SIMT=1
-// disables it (A/B comparisons, tools/tc_stats.py).
-template <class T> static bool use_tensor_cores(int H0, int H1) { return false; }
-template <> bool use_tensor_cores<float>(int H0, int H1) {
-    static int forced = -1;
-    if (forced < 0) { const char* e = getenv("PDDP_FORCE_SIMT"); forced = (e && e[0] == '1') ? 1 : 0; }
-    return !forced && H0 > 64 && H1 > 64 && H0 + 1 <= tc::MAX_NKB * tc::KB && H1 <= tc::TILE_N;
-}
-
 template <class T>
 static cudaError_t prep_weights(const pddp_shape* s, const pddp_bnn* n, const Workspace<T>& w, cudaStream_t st) {
     const int D = s->geo == GEO_PENDULUM ? 2 : s->geo == GEO_CARTPOLE ? 4 : 6;
@@ -515,74 +612,8 @@ static cudaError_t prep_weights(const pddp_shape* s, const pddp_bnn* n, const Wo
     bnn_transpose_kernel<T><<<8, 256, 0, st>>>((const T*)n->W2, 2 * D, n->H1, n->eps_out ? 2 * D : D, w.W2T);
     bnn_transpose_kernel<T><<<16, 256, 0, st>>>((const T*)n->mask0, n->P, n->H0, n->P, w.m0T);
     bnn_transpose_kernel<T><<<16, 256, 0, st>>>((const T*)n->mask1, n->P, n->H1, n->P, w.m1T);
-    if (use_tensor_cores<T>(n->H0, n->H1)) {
-        // PDDP_MLP_COMPACT=0 keeps every hidden unit (A/B measurements; the images are then the same for all particles)
-        static int compact = -1;
-        if (compact < 0) { const char* e = getenv("PDDP_MLP_COMPACT"); compact = (e && e[0] == '0') ? 0 : 1; }
-        int* meta = const_cast<int*>(w.im.meta);
-        tc::prep_index_kernel<<<(n->P + 63) / 64, 64, 0, st>>>((const float*)n->mask0, (const float*)n->mask1, n->P, n->H0, n->H1,
-                                                               compact, w.im.idx0, w.im.idx1, meta);
-        tc::prep_scale_kernel<<<1, 256, 0, st>>>((const float*)n->W1, (const float*)n->b1, n->H0, n->H1,
-                                                 const_cast<float*>(w.im.scale));
-        tc::prep_w1_kernel<<<592, 256, 0, st>>>((const float*)n->W1, (const float*)n->b1, n->P, n->H0, n->H1, w.im.idx0, w.im.idx1,
-                                                meta, w.im.scale, const_cast<unsigned char*>(w.im.W1img));
-        if (DA + 2 <= 8)
-            tc::prep_w0_kernel<8><<<64, 256, 0, st>>>((const float*)n->W0, (const float*)n->b0, (const float*)n->mask0,
-                                                       n->P, n->H0, DA + 1, w.im.idx0, meta, const_cast<unsigned char*>(w.im.W0img));
-        else
-            tc::prep_w0_kernel<16><<<64, 256, 0, st>>>((const float*)n->W0, (const float*)n->b0, (const float*)n->mask0,
-                                                        n->P, n->H0, DA + 1, w.im.idx0, meta, const_cast<unsigned char*>(w.im.W0img));
-        tc::prep_w2_kernel<<<64, 256, 0, st>>>((const float*)n->W2, (const float*)n->mask1, n->P, n->H1, D, D <= 4 ? 4 : 8,
-                                               w.im.idx1, meta, w.im.scale, const_cast<float*>(w.im.W2p));
-    }
+    if (use_tensor_cores<T>(n->H0, n->H1)) CK(bnn_mlp_prep_images(s->geo, n, w.im, st));
     return cudaGetLastError();
-}
-
-// MLP dispatch: SIMT kernel (the tcgen05 kernel hooks in here for fp32 / H = 200)
-template <class T, int GEO, bool TAN, int NJ, bool PSTD = false>
-static cudaError_t launch_mlp_simt(const BnnMlpArgs<T>& a, cudaStream_t st) {
-    constexpr int RPT = sizeof(T) == 4 ? 8 : 4;
-    typedef MlpSmem<T, GEO, NJ, RPT, TAN, PSTD> SM;
-    auto kern = bnn_mlp_simt_kernel<T, GEO, NJ, RPT, TAN, PSTD>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
-    if (e != cudaSuccess) return e;
-    const long long ntiles = (a.total + SM::NPART - 1) / SM::NPART;
-    const int grid = (int)(ntiles < (long long)num_sms() ? ntiles : (long long)num_sms());
-    kern<<<grid, 256, SM::bytes, st>>>(a);
-    return cudaGetLastError();
-}
-template <int GEO, bool TAN>
-static cudaError_t launch_mlp_tc(const BnnMlpArgs<float>& a, const tc::Images& im, cudaStream_t st) {
-    typedef Geo<GEO> G;
-    constexpr int K0P = G::DA + G::NU + 1 <= 8 ? 8 : 16, DP = G::D <= 4 ? 4 : 8;
-    auto kern = tc::bnn_mlp_tc_kernel<GEO, TAN>;
-    const int smem = tc::Cfg<K0P, DP>::TOTAL + tc::Cfg<K0P, DP>::ALIGN_PAD;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    const int S = (int)(a.total / a.net.P);                  // items per particle: (problem, alpha) pairs / problems
-    const int tiles_p = (S + tc::TILE_M - 1) / tc::TILE_M;      // super-tiles per particle (TAN: 1 + T passes each)
-    const long long ntiles = (long long)tiles_p * a.net.P;
-    if (ntiles >= (1ll << 31)) return cudaErrorInvalidValue;
-    const int grid = (int)(ntiles < (long long)num_sms() ? ntiles : (long long)num_sms());
-    kern<<<grid, tc::THREADS, smem, st>>>(a, im, S, tiles_p);
-    return cudaGetLastError();
-}
-template <class T, int GEO, bool TAN>
-static cudaError_t launch_mlp(const BnnMlpArgs<T>& a, const tc::Images& im, cudaStream_t st) {
-    const int H = a.net.H0 > a.net.H1 ? a.net.H0 : a.net.H1;
-    if (a.net.eps_out) {                     // use_predicted_std: both output heads, CUDA-core kernel
-        if (H <= 32) return launch_mlp_simt<T, GEO, TAN, 2, true>(a, st);
-        if (H <= 208) return launch_mlp_simt<T, GEO, TAN, 13, true>(a, st);
-        if (H <= 256) return launch_mlp_simt<T, GEO, TAN, 16, true>(a, st);
-        return cudaErrorInvalidValue;
-    }
-    if (use_tensor_cores<T>(a.net.H0, a.net.H1)) {
-        if constexpr (sizeof(T) == 4) return launch_mlp_tc<GEO, TAN>(a, im, st);
-    }
-    if (H <= 32) return launch_mlp_simt<T, GEO, TAN, 2>(a, st);
-    if (H <= 208) return launch_mlp_simt<T, GEO, TAN, 13>(a, st);
-    if (H <= 256) return launch_mlp_simt<T, GEO, TAN, 16>(a, st);
-    return cudaErrorInvalidValue;
 }
 
 struct BnnCall {
@@ -601,7 +632,6 @@ static void fill_cost_params(const pddp_cost* c, int DA, CostParams<T>& out) {
     for (int i = 0; i < MAX_NU; ++i) out.ug[i] = (T)c->u_goal[i];
 }
 
-#define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return e__; } while (0)
 
 template <class T>
 __global__ void bnn_set_z0_kernel(int B, int nz, const T* z0, T* Z, Layout lZ, const int32_t* active) {
@@ -640,9 +670,10 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
     MomentLinArgs<T> m;
     m.B = B; m.N = N; m.P = P; m.Jp = w.Jp; m.active = c.active; m.Z = Z; m.F_z = (T*)c.F_z; m.F_u = (T*)c.F_u;
     m.status = c.status; m.lZ = lZ; m.lFz = make_layout(ly, B, N, nz * nz); m.lFu = make_layout(ly, B, N, nz * nu);
-    const int wpb = 4;
-    const size_t msmem = (size_t)wpb * P * (3 * D + D * D) * sizeof(T);
-    auto mk = bnn_moment_lin_kernel<T, GEO, ENC>;
+    // warps per problem: two when there are more input directions than lanes (double cartpole, full covariance: 43)
+    constexpr int WPP = enc_size(D, ENC) + G::NU > 32 ? 2 : 1, ppb = 4 / WPP;
+    const size_t msmem = (size_t)ppb * moment_lin_smem_elems<D, WPP>(P) * sizeof(T);
+    auto mk = bnn_moment_lin_kernel<T, GEO, ENC, WPP>;
     CK(cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
 
     BnnMlpArgs<T> a;
@@ -657,11 +688,11 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
         a.X = cur; a.Xn = nxt;
         if (net.eps_out) a.net.eps_out = net.eps_out + (size_t)t * P * D;
         prof_begin(PROF_MLP_LIN, c.st);
-        CK((launch_mlp<T, GEO, true>(a, w.im, c.st)));
+        CK(bnn_mlp_launch<T>(GEO, true, a, w.im, c.st));
         prof_end(PROF_MLP_LIN, c.st);
         m.t = t; m.X = cur; m.Xn = nxt;
         prof_begin(PROF_MOMENT_LIN, c.st);
-        mk<<<(B + wpb - 1) / wpb, wpb * 32, msmem, c.st>>>(m);
+        mk<<<(B + ppb - 1) / ppb, 128, msmem, c.st>>>(m);
         prof_end(PROF_MOMENT_LIN, c.st);
         T* tmp = cur; cur = nxt; nxt = tmp;
     }
@@ -719,9 +750,16 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     const Layout lZall = make_layout(PDDP_PROBLEM_MAJOR, (int)S, N + 1, nz);
     bnn_init_particles_kernel<T, GEO, ENC><<<igrid, 128, 0, c.st>>>(r.Z, r.lZ, 0, A, A, S, P, eps_of(0), nullptr, 0,
                                                                     nullptr, w.Xa, c.status);
-    const unsigned rgrid = (unsigned)((S + 31) / 32);
+    // 8 lanes per (problem, alpha) pair while that grid fits the SMs in one wave, else 4 (cfg 2: 1 280 CTAs were 1.7 waves)
+    const size_t pair_bytes = (size_t)P * D * sizeof(T);
+    const bool lpp4 = (S + 31) / 32 > (long long)num_sms() * 4 && 64 * pair_bytes <= 100 * 1024;
+    const unsigned rgrid = (unsigned)(lpp4 ? (S + 63) / 64 : (S + 31) / 32);
+    const size_t rsmem = (lpp4 ? 64 : 32) * pair_bytes + 16;
+    if (rsmem > 200 * 1024) return cudaErrorInvalidValue;       // (particles of 32 pairs must fit shared memory)
+    auto roll_step = lpp4 ? bnn_roll_step_kernel<T, GEO, ENC, 4> : bnn_roll_step_kernel<T, GEO, ENC, 8>;
+    CK(cudaFuncSetAttribute(roll_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
     r.t = -1; r.Xn = w.Xa;
-    bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 256, 0, c.st>>>(r);
+    roll_step<<<rgrid, 256, rsmem, c.st>>>(r);
     CK(cudaGetLastError());
     BnnMlpArgs<T> a;
     a.net = net; a.u = w.ucur; a.Jp = nullptr; a.total = total;
@@ -730,11 +768,11 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
         a.X = cur; a.Xn = nxt;
         if (net.eps_out) a.net.eps_out = net.eps_out + (size_t)t * P * D;
         prof_begin(PROF_MLP_ROLL, c.st);
-        CK((launch_mlp<T, GEO, false>(a, w.im, c.st)));
+        CK(bnn_mlp_launch<T>(GEO, false, a, w.im, c.st));
         prof_end(PROF_MLP_ROLL, c.st);
         r.t = t; r.Xn = nxt;
         prof_begin(PROF_ROLL_STEP, c.st);
-        bnn_roll_step_kernel<T, GEO, ENC><<<rgrid, 256, 0, c.st>>>(r);
+        roll_step<<<rgrid, 256, rsmem, c.st>>>(r);
         prof_end(PROF_ROLL_STEP, c.st);
         if (mode != PDDP_BNN_INPUT_INFER && t + 1 < N)      // candidate particles of step t+1 from the z' just encoded
             bnn_init_particles_kernel<T, GEO, ENC><<<igrid, 128, 0, c.st>>>(w.Zall, lZall, t + 1, 1, A, S, P, eps_of(t + 1),
@@ -836,10 +874,3 @@ extern "C" int pddp_rollout_bnn(const pddp_shape* s, const pddp_bnn* n, const pd
     return pddp_capi_cuda(e, "pddp_rollout_bnn");
 }
 
-#ifdef PDDP_EXP_TRACE
-// (timeline experiment) copies CTA 0's trace of the last tcgen05 MLP launch to the host
-extern "C" int pddp_debug_trace(long long* dst, size_t n) {
-    cudaDeviceSynchronize();
-    return (int)cudaMemcpyFromSymbol(dst, pddp::tc::g_trace, n * sizeof(long long));
-}
-#endif

@@ -149,6 +149,29 @@ __device__ __forceinline__ bool encode_moments(const T* M, const T (&Cov)[D][D],
     return true;
 }
 
+// ---- 1-D bulk copy (TMA unit, cp.async.bulk) global -> shared with an mbarrier, for kernels that stage one contiguous
+// block per CTA: one request instead of a dependent chain of per-thread loads
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// bytes: a multiple of 16; src and dst 16-byte aligned
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr_u32(dst)), "l"(src), "r"(bytes), "r"(smem_addr_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "BULK_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 10000;\n\t"
+        "@p bra.uni BULK_WAIT_DONE;\n\t"
+        "bra.uni BULK_WAIT_LOOP;\n\t"
+        "BULK_WAIT_DONE:\n\t}" ::"r"(smem_addr_u32(bar)), "r"(parity) : "memory");
+}
+
 template <class T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

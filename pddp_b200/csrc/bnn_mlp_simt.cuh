@@ -11,19 +11,10 @@
 // One CTA = 16x16 threads owns a tile of RT = 16*RPT rows and all H columns; the H0xH1 layer is a
 // shared-memory-tiled FFMA GEMM (thread = RPT rows x NJ strided columns).
 #pragma once
-#include "bnn_common.cuh"
+#include "bnn_mlp_iface.h"
 
 namespace pddp {
 
-template <class T>
-struct BnnMlpArgs {
-    BnnNet<T> net;
-    const T* X;        // [S, P, D] particles in
-    const T* u;        // [S] action per particle group (nu == 1)
-    T* Xn;             // [S, P, D] particles out
-    T* Jp;             // [S, P, D, D+nu] per-particle Jacobian (TAN only)
-    long long total;   // S * P
-};
 
 constexpr int MLP_KC = 16;
 constexpr int MLP_KP = 16;   // padded layer-0 input width (K0 = DA + nu <= 9)

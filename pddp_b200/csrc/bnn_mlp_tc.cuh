@@ -315,6 +315,7 @@ __global__ void prep_scale_kernel(const float* W1, const float* b1, int H0, int 
 // layer-1 units}: the K range is the kept layer-0 units followed by the bias unit, rounded up to 16.
 constexpr float DROP_BELOW = 5.9604645e-8f;    // 2^-24
 constexpr int META = 4;
+static_assert(META == IMG_META, "bnn_mlp_iface.h sizes");
 __global__ void prep_index_kernel(const float* mask0 /*[P][H0]*/, const float* mask1 /*[P][H1]*/, int P, int H0, int H1,
                                   int compact, int* idx0 /*[P][TILE_N]*/, int* idx1 /*[P][TILE_N]*/, int* meta /*[P][META]*/) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -334,6 +335,7 @@ __global__ void prep_index_kernel(const float* mask0 /*[P][H0]*/, const float* m
 // unit idx1[p][c], K position q is kept layer-0 unit idx0[p][q], position n0 (the bias unit) carries b1.  Blocks sit
 // B_STAGE bytes apart; only the first N(p) * 64 bytes of a block are read.
 constexpr size_t W1_PSTRIDE = (size_t)13 * 208 * 64;       // MAX_NKB * B_STAGE
+static_assert(W1_PSTRIDE == IMG_W1_PSTRIDE && TILE_N == IMG_TILE_N, "bnn_mlp_iface.h sizes");
 __global__ void prep_w1_kernel(const float* W1 /*[H1][H0]*/, const float* b1, int P, int H0, int H1, const int* idx0,
                                const int* idx1, const int* meta, const float* scale, unsigned char* img) {
     const long long total = (long long)P * MAX_NKB * TILE_N * KB;
@@ -407,15 +409,6 @@ __global__ void prep_w2_kernel(const float* W2 /*[2D][H1]*/, const float* mask1 
     }
 }
 
-struct Images {
-    const unsigned char* W1img;   // [P] per-particle images, W1_PSTRIDE apart
-    const unsigned char* W0img;
-    const float* W2p;
-    const float* scale;        // [2]: power-of-two scale of the W1 image and its inverse
-    const int* meta;           // [P][META]: K-blocks, accumulator columns, kept units of layer 0 / layer 1
-    int* idx0;                 // [P][TILE_N] compaction lists (prep kernels only)
-    int* idx1;
-};
 
 // ---- tile schedule ------------------------------------------------------------------------------------------
 // The CTA owns super-tiles [T0, T1) (tau = particle * tiles_p + item block).  A SEGMENT is the run of super-tiles of

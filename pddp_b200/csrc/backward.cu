@@ -226,6 +226,14 @@ __device__ __forceinline__ void load4(const double* p, double (&v)[4]) {
     const double2 t0 = *reinterpret_cast<const double2*>(p), t1 = *reinterpret_cast<const double2*>(p + 2);
     v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
 }
+__device__ __forceinline__ void load2(const float* p, float (&v)[2]) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+}
+__device__ __forceinline__ void load2(const double* p, double (&v)[2]) {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    v[0] = t.x; v[1] = t.y;
+}
 __device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
@@ -236,7 +244,9 @@ __device__ __forceinline__ void store4(double* p, const double (&v)[4]) {
 // NZC > 0: encoded state size known at compile time (nz = 14: UT-Cholesky cartpole, nz = 42: full-covariance double
 // cartpole) -- the strip loops unroll and the index divisions fold away.
 template <class T, int TEAM, int NZC = 0>
-__global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(const BackwardArgs<T> a) {
+// (min blocks per SM 7: 4 096 problems at 4 per CTA, or 1 024 at one CTA each, are 6.9 CTAs per SM -- with the
+// 96 / 40 registers the compiler took by itself 5 / 6 were resident and a second, nearly empty wave cost 15 - 38 %)
+__global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM, sizeof(T) == 4 ? 7 : 1) backward_warp_kernel(const BackwardArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x % TEAM, warp = threadIdx.x / TEAM, wpb = blockDim.x / TEAM;
     const int b = blockIdx.x * wpb + warp;
@@ -245,7 +255,12 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(
     // rows padded to LD (a multiple of 4) so that a thread can own a 1 x 4 strip of an output row and
     // read its B operand with one 16-byte LDS per 4 FMAs (an element per thread needs 2 LDS per FMA,
     // and at nz = 42 the pass was bound by shared-memory loads)
-    const int nz = NZC > 0 ? NZC : a.nz, nn = nz * nz, LD = (nz + 3) & ~3, NS4 = LD / 4, nl = nz * LD;
+    // Register tile: 2 rows x 4 columns per thread.  Both products read their A operand DOWN a column of a row-major
+    // matrix (W = V Fz through VT[kk][i] = V[i][kk]: V is kept TRANSPOSED -- it is symmetric after the first step and
+    // the terminal L_zz is stored transposed below --; Q_zz = Fz^T W through Fz[kk][i]), so the two A values of a tile
+    // are one 8-byte LDS: 6 shared-memory wavefronts and 10 instructions per 8 FMAs instead of 5 and 6 per 4 (the
+    // nz = 42 pass was bound by the shared-memory pipe, the nz = 14 pass needed two rounds of 1 x 4 strips per product).
+    const int nz = NZC > 0 ? NZC : a.nz, nn = nz * nz, LD = (nz + 3) & ~3, NS4 = LD / 4, nl = nz * LD, NR2 = (nz + 1) / 2;
     const int per_team = backward_team_elems(nz);
     T* base = reinterpret_cast<T*>(smem_raw) + (size_t)warp * per_team;
     T *V = base, *Fz = base + nl, *W = base + 2 * nl;
@@ -257,7 +272,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(
     T lo = T(0), hi = T(0);
     if (bounded) { lo = a.u_min[0]; hi = a.u_max[0]; }
 
-    for (int e = lane; e < nn; e += TEAM) V[(e / nz) * LD + e % nz] = a.L_zz[a.lLzz.at(b, a.N, e)];
+    for (int e = lane; e < nn; e += TEAM) V[(e % nz) * LD + e / nz] = a.L_zz[a.lLzz.at(b, a.N, e)];   // V^T
     for (int e = lane; e < nz; e += TEAM) v[e] = a.L_z[a.lLz.at(b, a.N, e)];
     team_sync<TEAM>();
     T k_next = T(0);
@@ -267,21 +282,24 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(
         for (int e = lane; e < nz; e += TEAM) Fu[e] = a.F_u[a.lFu.at(b, t, e)];
         team_sync<TEAM>();
         // W = V Fz ; wu = V Fu
-        for (int s4 = lane; s4 < nz * NS4; s4 += TEAM) {
-            const int i = s4 / NS4, j0 = (s4 - i * NS4) * 4;
-            T acc[4] = {T(0), T(0), T(0), T(0)};
+        for (int s4 = lane; s4 < NR2 * NS4; s4 += TEAM) {
+            const int i0 = (s4 / NS4) * 2, j0 = (s4 % NS4) * 4;
+            T acc[2][4] = {{T(0), T(0), T(0), T(0)}, {T(0), T(0), T(0), T(0)}};
             for (int kk = 0; kk < nz; ++kk) {
-                const T av = V[i * LD + kk];
-                T bv[4];
+                T av[2], bv[4];
+                load2(V + kk * LD + i0, av);                     // V[i0][kk], V[i0 + 1][kk]  (row i0 + 1 == nz: zero padding)
                 load4(Fz + kk * LD + j0, bv);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[c] += av * bv[c];
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[r][c] += av[r] * bv[c];
             }
-            store4(W + i * LD + j0, acc);
+            store4(W + i0 * LD + j0, acc[0]);
+            if (i0 + 1 < nz) store4(W + (i0 + 1) * LD + j0, acc[1]);
         }
         for (int i = lane; i < nz; i += TEAM) {
             T s = T(0);
-            for (int kk = 0; kk < nz; ++kk) s += V[i * LD + kk] * Fu[kk];
+            for (int kk = 0; kk < nz; ++kk) s += V[kk * LD + i] * Fu[kk];
             wu[i] = s;
         }
         team_sync<TEAM>();
@@ -302,19 +320,25 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM) backward_warp_kernel(
         }
         team_sync<TEAM>();
         // Q_zz = L_zz + Fz^T W  -> overwrites V (V is dead once W and wu exist)
-        for (int s4 = lane; s4 < nz * NS4; s4 += TEAM) {
-            const int i = s4 / NS4, j0 = (s4 - i * NS4) * 4;
-            T acc[4];
+        for (int s4 = lane; s4 < NR2 * NS4; s4 += TEAM) {
+            const int i0 = (s4 / NS4) * 2, j0 = (s4 % NS4) * 4;
+            T acc[2][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c] = j0 + c < nz ? a.L_zz[a.lLzz.at(b, t, i * nz + j0 + c)] : T(0);
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    acc[r][c] = (i0 + r < nz && j0 + c < nz) ? a.L_zz[a.lLzz.at(b, t, (i0 + r) * nz + j0 + c)] : T(0);
             for (int kk = 0; kk < nz; ++kk) {
-                const T av = Fz[kk * LD + i];
-                T bv[4];
+                T av[2], bv[4];
+                load2(Fz + kk * LD + i0, av);
                 load4(W + kk * LD + j0, bv);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[c] += av * bv[c];
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[r][c] += av[r] * bv[c];
             }
-            store4(V + i * LD + j0, acc);
+            store4(V + i0 * LD + j0, acc[0]);                    // Q_zz, row-major; symmetrised below
+            if (i0 + 1 < nz) store4(V + (i0 + 1) * LD + j0, acc[1]);
         }
         T kt, inv;
         T ut = bounded ? a.U[a.lU.at(b, t, 0)] : T(0);

@@ -118,8 +118,19 @@ PDDP_HD void decode_var(const S* z, S (&V)[D]) {
 // The reference re-encodes the augmented moments (a Cholesky for UT) and decodes them again inside
 // QRCost; U^T U == C (+1e-12 I jitter) so the round trip is the identity and is not replayed here.
 // l_x(z) only; the action term du^T R du is separable (L_uz == 0) and handled by the caller.
+// sine / cosine of the angular components of a state: evaluated ONCE per state and shared by the cost and the
+// dynamics of the same step (the rollout of the closed-form models is bound by instruction issue, and the three
+// separate sinf / cosf calls per pendulum step were a third of it)
+template <int GEO, class S>
+struct StateTrig { S s[Geo<GEO>::NANG], c[Geo<GEO>::NANG]; };
+template <int GEO, class S>
+PDDP_HD void state_trig(const S* z, StateTrig<GEO, S>& tr) {
+#pragma unroll
+    for (int i = 0; i < Geo<GEO>::NANG; ++i) jsincos(z[Geo<GEO>::ang(i)], tr.s[i], tr.c[i]);
+}
+
 template <int GEO, int ENC, class T, class S>
-PDDP_HD S cost_state(const CostParams<T>& cp, const S* z, bool terminal) {
+PDDP_HD S cost_state(const CostParams<T>& cp, const S* z, bool terminal, const StateTrig<GEO, S>& tr) {
     typedef Geo<GEO> G;
     constexpr int D = G::D, DA = G::DA, NNA = G::NNA, NANG = G::NANG;
     const T* Q = terminal ? cp.Qt : cp.Q;
@@ -130,8 +141,8 @@ PDDP_HD S cost_state(const CostParams<T>& cp, const S* z, bool terminal) {
         for (int i = 0; i < NNA; ++i) Ma[i] = z[G::nonang(i)];
 #pragma unroll
         for (int i = 0; i < NANG; ++i) {
-            Ma[NNA + 2 * i] = jsin(z[G::ang(i)]);
-            Ma[NNA + 2 * i + 1] = jcos(z[G::ang(i)]);
+            Ma[NNA + 2 * i] = tr.s[i];
+            Ma[NNA + 2 * i + 1] = tr.c[i];
         }
         S val = S(T(0));
 #pragma unroll
@@ -150,8 +161,8 @@ PDDP_HD S cost_state(const CostParams<T>& cp, const S* z, bool terminal) {
 #pragma unroll
     for (int i = 0; i < NANG; ++i) {
         S damp = jexp(C[G::ang(i)][G::ang(i)] * T(-0.5));
-        sn[i] = damp * jsin(z[G::ang(i)]);
-        cs[i] = damp * jcos(z[G::ang(i)]);
+        sn[i] = damp * tr.s[i];
+        cs[i] = damp * tr.c[i];
         Ma[NNA + 2 * i] = sn[i];
         Ma[NNA + 2 * i + 1] = cs[i];
     }
@@ -191,17 +202,27 @@ PDDP_HD S cost_state(const CostParams<T>& cp, const S* z, bool terminal) {
             S q = jexp(lq);
             S ep = jexp(lq + cij) - q, em = jexp(lq - cij) - q;
             S dm = z[G::ang(i)] - z[G::ang(j)], sm = z[G::ang(i)] + z[G::ang(j)];
-            S U3 = ep * jcos(dm), U4 = em * jcos(sm);
+            S sdm, cdm, ssm, csm;
+            jsincos(dm, sdm, cdm);
+            jsincos(sm, ssm, csm);
+            S U3 = ep * cdm, U4 = em * csm;
             const int si = NNA + 2 * i, ci = si + 1, sj = NNA + 2 * j, cj = sj + 1;
             // Va[si][sj] = .5(U3-U4), Va[ci][cj] = .5(U3+U4); multiplied by Q[sj][si], Q[cj][ci]
             val = val + (U3 - U4) * (T(0.5) * Q[sj * DA + si]) + (U3 + U4) * (T(0.5) * Q[cj * DA + ci]);
             if (ENC == ENC_FULL || ENC == ENC_UT) {
-                S U1 = ep * jsin(dm), U2 = em * jsin(sm);
+                S U1 = ep * sdm, U2 = em * ssm;
                 // Va[si][cj] = .5(U1+U2)[i][j] times Q[cj][si]; Va[cj][si] (transpose) times Q[si][cj]
                 val = val + (U1 + U2) * (T(0.5) * (Q[cj * DA + si] + Q[si * DA + cj]));
             }
         }
     return val;
+}
+
+template <int GEO, int ENC, class T, class S>
+PDDP_HD S cost_state(const CostParams<T>& cp, const S* z, bool terminal) {
+    StateTrig<GEO, S> tr;
+    state_trig<GEO, S>(z, tr);
+    return cost_state<GEO, ENC, T, S>(cp, z, terminal, tr);
 }
 
 // action part of the cost: value, gradient, Hessian (NU == 1)   ref: costs/quadratic.py:86-89
@@ -218,17 +239,17 @@ template <class T>
 struct KnownParams { T p[8]; };   // pendulum: dt,m,l,mu,g | cartpole: dt,mc,mp,l,mu,g | double: dt,mc,mp1,mp2,l1,l2,mu,g
 
 template <int GEO, class T, class S>
-PDDP_HD void known_mean_step(const KnownParams<T>& kp, const S* x, const S& u, S* xn) {
+PDDP_HD void known_mean_step(const KnownParams<T>& kp, const S* x, const S& u, S* xn, const StateTrig<GEO, S>& tr) {
     const T* p = kp.p;
     if (GEO == GEO_PENDULUM) {                            // ref: examples/pendulum/model.py:84-119
         T dt = p[0], m = p[1], l = p[2], mu = p[3], g = p[4];
         T ml = m * l;
-        S acc = (u - x[1] * mu - jsin(x[0]) * (T(0.5) * ml * g)) * (T(3) / (ml * l));
+        S acc = (u - x[1] * mu - tr.s[0] * (T(0.5) * ml * g)) * (T(3) / (ml * l));
         xn[0] = x[0] + x[1] * dt;
         xn[1] = x[1] + acc * dt;
     } else if (GEO == GEO_CARTPOLE) {                     // ref: examples/cartpole/model.py:88-141
         T dt = p[0], mc = p[1], mp = p[2], l = p[3], mu = p[4], g = p[5];
-        S s = jsin(x[2]), c = jcos(x[2]);
+        S s = tr.s[0], c = tr.c[0];
         S a0 = x[3] * x[3] * s * (mp * l);
         S a1 = s * g;
         S a2 = u - x[1] * mu;
@@ -242,8 +263,9 @@ PDDP_HD void known_mean_step(const KnownParams<T>& kp, const S* x, const S& u, S
         xn[3] = nthd;
     } else {                                              // ref: examples/double_cartpole/model.py:100-195
         T dt = p[0], mc = p[1], mp1 = p[2], mp2 = p[3], l1 = p[4], l2 = p[5], mu = p[6], g = p[7];
-        S s1 = jsin(x[2]), c1 = jcos(x[2]), s2 = jsin(x[4]), c2 = jcos(x[4]);
-        S sd = jsin(x[2] - x[4]), cd = jcos(x[2] - x[4]);
+        S s1 = tr.s[0], c1 = tr.c[0], s2 = tr.s[1], c2 = tr.c[1];
+        S sd, cd;
+        jsincos(x[2] - x[4], sd, cd);
         T a0 = mp2 + T(2) * mc, a1 = mc * l2;
         S a2 = x[3] * x[3] * l1, a3 = x[5] * x[5] * a1;
         // A sol = b, rows as in the reference
@@ -267,6 +289,13 @@ PDDP_HD void known_mean_step(const KnownParams<T>& kp, const S* x, const S& u, S
         xn[4] = x[4] + n2 * dt;
         xn[5] = n2;
     }
+}
+
+template <int GEO, class T, class S>
+PDDP_HD void known_mean_step(const KnownParams<T>& kp, const S* x, const S& u, S* xn) {
+    StateTrig<GEO, S> tr;
+    state_trig<GEO, S>(x, tr);
+    known_mean_step<GEO, T, S>(kp, x, u, xn, tr);
 }
 
 // Known models pass the variance through unchanged and drop off-diagonal covariance

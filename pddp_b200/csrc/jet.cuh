@@ -18,6 +18,9 @@ PDDP_HD float jsin(float x) { return sinf(x); }
 PDDP_HD double jsin(double x) { return sin(x); }
 PDDP_HD float jcos(float x) { return cosf(x); }
 PDDP_HD double jcos(double x) { return cos(x); }
+// sine and cosine of one argument with ONE range reduction
+PDDP_HD void jsincos(float x, float& s, float& c) { sincosf(x, &s, &c); }
+PDDP_HD void jsincos(double x, double& s, double& c) { sincos(x, &s, &c); }
 PDDP_HD float jexp(float x) { return expf(x); }
 PDDP_HD double jexp(double x) { return exp(x); }
 PDDP_HD float jsqrt(float x) { return sqrtf(x); }
@@ -100,8 +103,14 @@ template <class T, int N> PDDP_HD Jet1<T, N> operator*(const Jet1<T, N>& a, T s)
 template <class T, int N> PDDP_HD Jet1<T, N> operator*(T s, const Jet1<T, N>& a) { return a * s; }
 template <class T, int N> PDDP_HD Jet1<T, N> operator/(const Jet1<T, N>& a, T s) { return a * (T(1) / s); }
 template <class T, int N> PDDP_HD Jet1<T, N> operator/(T s, const Jet1<T, N>& a) { return Jet1<T, N>(s) / a; }
-template <class T, int N> PDDP_HD Jet1<T, N> jsin(const Jet1<T, N>& a) { return chain(a, jsin(a.v), jcos(a.v)); }
-template <class T, int N> PDDP_HD Jet1<T, N> jcos(const Jet1<T, N>& a) { return chain(a, jcos(a.v), -jsin(a.v)); }
+template <class T, int N> PDDP_HD Jet1<T, N> jsin(const Jet1<T, N>& a) { T s, c; jsincos(a.v, s, c); return chain(a, s, c); }
+template <class T, int N> PDDP_HD Jet1<T, N> jcos(const Jet1<T, N>& a) { T s, c; jsincos(a.v, s, c); return chain(a, c, -s); }
+template <class T, int N> PDDP_HD void jsincos(const Jet1<T, N>& a, Jet1<T, N>& sn, Jet1<T, N>& cs) {
+    T s, c;
+    jsincos(a.v, s, c);
+    sn = chain(a, s, c);
+    cs = chain(a, c, -s);
+}
 template <class T, int N> PDDP_HD Jet1<T, N> jexp(const Jet1<T, N>& a) { T e = jexp(a.v); return chain(a, e, e); }
 template <class T, int N> PDDP_HD Jet1<T, N> jsqrt(const Jet1<T, N>& a) { T s = jsqrt(a.v); return chain(a, s, T(0.5) / s); }
 template <class T, int N> PDDP_HD T jvalue(const Jet1<T, N>& a) { return a.v; }
@@ -196,8 +205,14 @@ template <class T, int N> PDDP_HD Jet2<T, N> operator*(const Jet2<T, N>& a, T s)
 template <class T, int N> PDDP_HD Jet2<T, N> operator*(T s, const Jet2<T, N>& a) { return a * s; }
 template <class T, int N> PDDP_HD Jet2<T, N> operator/(const Jet2<T, N>& a, T s) { return a * (T(1) / s); }
 template <class T, int N> PDDP_HD Jet2<T, N> operator/(T s, const Jet2<T, N>& a) { return jrecip(a) * s; }
-template <class T, int N> PDDP_HD Jet2<T, N> jsin(const Jet2<T, N>& a) { T s = jsin(a.v), c = jcos(a.v); return chain(a, s, c, -s); }
-template <class T, int N> PDDP_HD Jet2<T, N> jcos(const Jet2<T, N>& a) { T s = jsin(a.v), c = jcos(a.v); return chain(a, c, -s, -c); }
+template <class T, int N> PDDP_HD Jet2<T, N> jsin(const Jet2<T, N>& a) { T s, c; jsincos(a.v, s, c); return chain(a, s, c, -s); }
+template <class T, int N> PDDP_HD Jet2<T, N> jcos(const Jet2<T, N>& a) { T s, c; jsincos(a.v, s, c); return chain(a, c, -s, -c); }
+template <class T, int N> PDDP_HD void jsincos(const Jet2<T, N>& a, Jet2<T, N>& sn, Jet2<T, N>& cs) {
+    T s, c;
+    jsincos(a.v, s, c);
+    sn = chain(a, s, c, -s);
+    cs = chain(a, c, -s, -c);
+}
 template <class T, int N> PDDP_HD Jet2<T, N> jexp(const Jet2<T, N>& a) { T e = jexp(a.v); return chain(a, e, e, e); }
 template <class T, int N> PDDP_HD Jet2<T, N> jsqrt(const Jet2<T, N>& a) {
     T s = jsqrt(a.v);

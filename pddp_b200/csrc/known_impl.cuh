@@ -173,13 +173,16 @@ __device__ __forceinline__ T roll_one(const RollKnownArgs<T>& a, int b, T alpha,
 #pragma unroll
             for (int e = 0; e < NZ; ++e) a.Z_new[a.lZ.at(b, t, e)] = z[e];
             a.U_new[a.lU.at(b, t, 0)] = u;
-        } else {
+        }
+        StateTrig<GEO, T> tr;                               // shared by the cost and the dynamics of this step
+        state_trig<GEO, T>(z, tr);
+        if (!STORE) {
             T la, lu, luu;
             cost_action(a.cost, u, la, lu, luu);
-            J += cost_state<GEO, ENC, T, T>(a.cost, z, false) + la;
+            J += cost_state<GEO, ENC, T, T>(a.cost, z, false, tr) + la;
         }
         T zn[NZ];
-        known_mean_step<GEO, T, T>(a.dyn, z, u, zn);
+        known_mean_step<GEO, T, T>(a.dyn, z, u, zn, tr);
         known_uncertainty_step<D, ENC, T>(z, zn);
 #pragma unroll
         for (int e = 0; e < NZ; ++e) z[e] = zn[e];

@@ -253,10 +253,86 @@ __device__ __forceinline__ int boxqp_n(int n, const T (&x0)[MNU], const T (&Q)[M
     return result;
 }
 
-// shared memory per team: three nz x LD matrices, two LD vectors, four nu x LD matrices, 32 small values
+// The small dense part of one time step (team-uniform inputs): eigen-clipped regularised Q_uu, feed-forward term kt
+// (unconstrained: -Q_uu_reg^-1 Q_u; bounded: box QP warm-started at k[t+1]) and M with K = -M Q_uz (the regularised
+// inverse restricted to the free dimensions).  false where the reference raises (ilqr.py:636-640, 653-655).
+template <class T>
+__device__ __forceinline__ bool solve_small(int nu, bool bounded, const T (&Quu)[MNU][MNU], const T (&Qu)[MNU], T reg,
+                                            const T (&lot)[MNU], const T (&hit)[MNU], const T (&k_next)[MNU],
+                                            T (&kt)[MNU], T (&M)[MNU][MNU]) {
+    T A[MNU][MNU], E[MNU][MNU], ev[MNU];
+    bool finite = true, ok = true;
+#pragma unroll
+    for (int i = 0; i < MNU; ++i)
+#pragma unroll
+        for (int j = 0; j < MNU; ++j) {
+            A[i][j] = Quu[i][j];
+            finite = finite && isfinite(Quu[i][j]);
+        }
+    if (!finite) return false;                             // linalg.eig raises on NaN / Inf
+    // (A Cholesky test for "Q_uu is already positive definite, skip the eigen-decomposition" was tried and
+    // measured SLOWER on the rendezvous workload: 40.6 vs 30.5 ms.  With R = 0.1 I the symmetric problem's Q_uu is
+    // diagonal up to rounding and the Jacobi loop exits before its first rotation, while the extra factorisation
+    // costs square roots, divisions and registers.)
+    jacobi_eig(nu, A, E, ev);
+#pragma unroll
+    for (int i = 0; i < MNU; ++i) {
+        if (ev[i] < T(0)) ev[i] = T(1e-12);                // ref: ilqr.py:633-634
+        ev[i] += reg;
+    }
+    if (!bounded) {
+#pragma unroll
+        for (int i = 0; i < MNU; ++i)
+#pragma unroll
+            for (int j = 0; j < MNU; ++j) {
+                T sum = T(0);
+#pragma unroll
+                for (int m = 0; m < MNU; ++m)
+                    if (m < nu) sum += (E[i][m] / ev[m]) * E[j][m];
+                M[i][j] = (i < nu && j < nu) ? sum : T(0);
+            }
+#pragma unroll
+        for (int i = 0; i < MNU; ++i) {
+            T sum = T(0);
+#pragma unroll
+            for (int j = 0; j < MNU; ++j) sum += M[i][j] * Qu[j];
+            kt[i] = -sum;
+            if (kt[i] != kt[i]) ok = false;
+        }
+    } else {
+        T Qreg[MNU][MNU], Uf[MNU][MNU];
+#pragma unroll
+        for (int i = 0; i < MNU; ++i)
+#pragma unroll
+            for (int j = 0; j < MNU; ++j) {
+                T sum = T(0);
+#pragma unroll
+                for (int m = 0; m < MNU; ++m)
+                    if (m < nu) sum += (E[i][m] * ev[m]) * E[j][m];
+                Qreg[i][j] = sum;
+            }
+        unsigned free;
+        const int result = boxqp_n(nu, k_next, Qreg, Qu, lot, hit, kt, free, Uf);
+        if (result < 1) ok = false;                        // ref: ilqr.py:653-655
+        // M = (Q_uu_reg[free, free])^-1 scattered back, zero rows / columns for the clamped dims
+#pragma unroll
+        for (int j = 0; j < MNU; ++j) {
+            T r[MNU], x[MNU];
+#pragma unroll
+            for (int i = 0; i < MNU; ++i) r[i] = (i == j && ((free >> j) & 1u)) ? T(1) : T(0);
+            chol_solve(Uf, r, x);
+#pragma unroll
+            for (int i = 0; i < MNU; ++i) M[i][j] = (((free >> i) & 1u) && ((free >> j) & 1u)) ? x[i] : T(0);
+        }
+    }
+    return ok;
+}
+
+// shared memory per team: three nz x LD matrices, two LD vectors, four nu x LD matrices, 64 small values
+// (Q_uu 16, Q_u 4 | hand-off results: kt 4, M 16, ok 1)
 __host__ __device__ inline int backward_nu_elems(int nz, int nu) {
     const int LD = (nz + 3) & ~3;
-    return 3 * nz * LD + 2 * LD + 4 * nu * LD + 32;
+    return 3 * nz * LD + 2 * LD + 4 * nu * LD + 64;
 }
 // stride between the teams of a CTA: == TEAM (mod 32) words, so that the 32 / TEAM teams of a warp, whose lanes read
 // TEAM consecutive words (or one broadcast word) at the same offset of their own region, hit 32 different banks
@@ -268,21 +344,31 @@ __host__ __device__ inline int backward_nu_stride(int nz, int nu, int team) {
 
 // NZC / NUC > 0: state / action sizes known at compile time (the loops unroll and the index divisions become shifts:
 // with run-time sizes the matrix phases of the rendezvous problem were 9.6 k instructions per warp and time step).
-template <class T, int TEAM, int NZC = 0, int NUC = 0>
-__global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM) backward_nu_kernel(const BackwardArgs<T> a) {
+//
+// HO (hand-off, sub-warp teams only): the small dense part is data dependent (Jacobi sweeps, box-QP iterations) and
+// team-uniform, so a warp of 32 / TEAM teams paid the union of its problems' paths once per 32 / TEAM problems: for
+// the rendezvous shape 6.8 k of the 10 k instructions per warp and time step.  With HO every team parks Q_uu / Q_u in
+// its shared-memory region and ONE warp of the CTA solves all of the CTA's problems, a problem per lane (the warm
+// start k[t+1] stays in that lane's registers); the other warps wait at the CTA barrier (other CTAs of the SM run
+// their matrix phases meanwhile).  Teams without work (b >= B, inactive, failed) keep taking part in the barriers.
+template <class T, int TEAM, int NZC = 0, int NUC = 0, bool HO = false>
+__global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM, (HO && sizeof(T) == 4) ? 4 : 1) backward_nu_kernel(const BackwardArgs<T> a) {
+    static_assert(!HO || TEAM < 32, "hand-off is for sub-warp teams");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x % TEAM, warp = threadIdx.x / TEAM, wpb = blockDim.x / TEAM;
     const int b = blockIdx.x * wpb + warp;
-    if (b >= a.B) return;
-    if (a.active && a.active[b] == 0) return;
+    const bool alive = b < a.B && !(a.active && a.active[b] == 0);
+    if (!HO && !alive) return;
     const int nz = NZC > 0 ? NZC : a.nz, nu = NUC > 0 ? NUC : a.nu, nn = nz * nz, LD = (nz + 3) & ~3, nl = nz * LD;
-    T* base = reinterpret_cast<T*>(smem_raw) + (size_t)warp * backward_nu_stride(nz, nu, TEAM);
+    const int stride = backward_nu_stride(nz, nu, TEAM);
+    T* base = reinterpret_cast<T*>(smem_raw) + (size_t)warp * stride;
     T *V = base, *Fz = base + nl, *W = base + 2 * nl;
     T *v = base + 3 * nl, *Qz = v + LD;
     T *FuT = Qz + LD, *WuT = FuT + nu * LD, *Quz = WuT + nu * LD, *Kt = Quz + nu * LD;   // [nu][LD], row = control dim
-    T *sQuu = Kt + nu * LD, *sQu = sQuu + 16;
+    T *sQuu = Kt + nu * LD, *sQu = sQuu + 16, *sKt = sQu + 4, *sM = sKt + 4, *sOk = sM + 16;
+    const int small_off = (int)(sQuu - base);
     const bool bounded = a.u_min != nullptr && a.u_max != nullptr;
-    const T reg = (T)a.mu[b];
+    const T reg = alive ? (T)a.mu[b] : T(0);
     T lo[MNU], hi[MNU], k_next[MNU];
 #pragma unroll
     for (int i = 0; i < MNU; ++i) {
@@ -290,203 +376,213 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM) backward_nu_kernel(co
         hi[i] = bounded && i < nu ? a.u_max[i] : T(0);
         k_next[i] = T(0);                                     // ref: ilqr.py:649 -- k[-1] is still zero at t = N-1
     }
-    for (int e = lane; e < nn; e += TEAM) V[(e / nz) * LD + e % nz] = a.L_zz[a.lLzz.at(b, a.N, e)];
-    for (int e = lane; e < nz; e += TEAM) v[e] = a.L_z[a.lLz.at(b, a.N, e)];
+    // hand-off: the problem this thread SOLVES (threads 0 .. wpb-1 of the CTA), its regularisation and warm start
+    const int sb = blockIdx.x * wpb + (int)threadIdx.x;
+    const bool solver = HO && (int)threadIdx.x < wpb;
+    const bool s_alive = solver && sb < a.B && !(a.active && a.active[sb] == 0);
+    const T s_reg = s_alive ? (T)a.mu[sb] : T(0);
+    T* s_small = reinterpret_cast<T*>(smem_raw) + (size_t)(solver ? threadIdx.x : 0) * stride + small_off;
+    if (alive) {
+        for (int e = lane; e < nn; e += TEAM) V[(e / nz) * LD + e % nz] = a.L_zz[a.lLzz.at(b, a.N, e)];
+        for (int e = lane; e < nz; e += TEAM) v[e] = a.L_z[a.lLz.at(b, a.N, e)];
+    }
+    if (HO && lane == 0) sOk[1] = alive ? T(1) : T(0);        // "this team has work at the next hand-off"
     nu_team_sync<TEAM>();
     bool ok = true;
     for (int t = a.N - 1; t >= 0; --t) {
-        for (int e = lane; e < nn; e += TEAM) Fz[(e / nz) * LD + e % nz] = a.F_z[a.lFz.at(b, t, e)];
-        for (int e = lane; e < nz * nu; e += TEAM) FuT[(e % nu) * LD + e / nu] = a.F_u[a.lFu.at(b, t, e)];
+        const bool work = alive && ok;                        // (without hand-off a team without work has left)
+        if (work) {
+            for (int e = lane; e < nn; e += TEAM) Fz[(e / nz) * LD + e % nz] = a.F_z[a.lFz.at(b, t, e)];
+            for (int e = lane; e < nz * nu; e += TEAM) FuT[(e % nu) * LD + e / nu] = a.F_u[a.lFu.at(b, t, e)];
+        }
         nu_team_sync<TEAM>();
         // W = V Fz ; WuT[i] = V Fu[:, i]
-        for (int e = lane; e < nn; e += TEAM) {
-            const int i = e / nz, j = e - i * nz;
-            T s = T(0);
-            for (int kk = 0; kk < nz; ++kk) s += V[i * LD + kk] * Fz[kk * LD + j];
-            W[i * LD + j] = s;
-        }
-        for (int e = lane; e < nz * nu; e += TEAM) {
-            const int i = e / nz, r = e - i * nz;
-            T s = T(0);
-            for (int kk = 0; kk < nz; ++kk) s += V[r * LD + kk] * FuT[i * LD + kk];
-            WuT[i * LD + r] = s;
+        if (work) {
+            for (int e = lane; e < nn; e += TEAM) {
+                const int i = e / nz, j = e - i * nz;
+                T s = T(0);
+                for (int kk = 0; kk < nz; ++kk) s += V[i * LD + kk] * Fz[kk * LD + j];
+                W[i * LD + j] = s;
+            }
+            for (int e = lane; e < nz * nu; e += TEAM) {
+                const int i = e / nz, r = e - i * nz;
+                T s = T(0);
+                for (int kk = 0; kk < nz; ++kk) s += V[r * LD + kk] * FuT[i * LD + kk];
+                WuT[i * LD + r] = s;
+            }
         }
         nu_team_sync<TEAM>();
         // Q_z, Q_uz, Q_u, Q_uu   (ref: ilqr.py:489-526)
-        for (int i = lane; i < nz; i += TEAM) {
-            T sz = a.L_z[a.lLz.at(b, t, i)];
-            for (int kk = 0; kk < nz; ++kk) sz += Fz[kk * LD + i] * v[kk];
-            Qz[i] = sz;
-        }
-        for (int e = lane; e < nz * nu; e += TEAM) {
-            const int i = e / nz, c = e - i * nz;
-            T s = a.L_uz[a.lLuz.at(b, t, i * nz + c)];
-            for (int kk = 0; kk < nz; ++kk) s += FuT[i * LD + kk] * W[kk * LD + c];
-            Quz[i * LD + c] = s;
-        }
-        for (int e = lane; e < nu * nu + nu; e += TEAM) {
-            if (e < nu * nu) {
-                const int i = e / nu, j = e - i * nu;
-                T s = a.L_uu[a.lLuu.at(b, t, e)];
-                for (int kk = 0; kk < nz; ++kk) s += FuT[i * LD + kk] * WuT[j * LD + kk];
-                sQuu[i * MNU + j] = s;
-            } else {
-                const int i = e - nu * nu;
-                T s = a.L_u[a.lLu.at(b, t, i)];
-                for (int kk = 0; kk < nz; ++kk) s += FuT[i * LD + kk] * v[kk];
-                sQu[i] = s;
+        if (work) {
+            for (int i = lane; i < nz; i += TEAM) {
+                T sz = a.L_z[a.lLz.at(b, t, i)];
+                for (int kk = 0; kk < nz; ++kk) sz += Fz[kk * LD + i] * v[kk];
+                Qz[i] = sz;
+            }
+            for (int e = lane; e < nz * nu; e += TEAM) {
+                const int i = e / nz, c = e - i * nz;
+                T s = a.L_uz[a.lLuz.at(b, t, i * nz + c)];
+                for (int kk = 0; kk < nz; ++kk) s += FuT[i * LD + kk] * W[kk * LD + c];
+                Quz[i * LD + c] = s;
+            }
+            for (int e = lane; e < nu * nu + nu; e += TEAM) {
+                if (e < nu * nu) {
+                    const int i = e / nu, j = e - i * nu;
+                    T s = a.L_uu[a.lLuu.at(b, t, e)];
+                    for (int kk = 0; kk < nz; ++kk) s += FuT[i * LD + kk] * WuT[j * LD + kk];
+                    sQuu[i * MNU + j] = s;
+                } else {
+                    const int i = e - nu * nu;
+                    T s = a.L_u[a.lLu.at(b, t, i)];
+                    for (int kk = 0; kk < nz; ++kk) s += FuT[i * LD + kk] * v[kk];
+                    sQu[i] = s;
+                }
             }
         }
         nu_team_sync<TEAM>();
         // Q_zz = L_zz + Fz^T W -> overwrites V (dead once W and WuT exist)
-        for (int e = lane; e < nn; e += TEAM) {
-            const int i = e / nz, j = e - i * nz;
-            T s = a.L_zz[a.lLzz.at(b, t, e)];
-            for (int kk = 0; kk < nz; ++kk) s += Fz[kk * LD + i] * W[kk * LD + j];
-            V[i * LD + j] = s;
-        }
-        // ---- small dense part, team-uniform ----
-        T Quu[MNU][MNU], Qu[MNU], A[MNU][MNU], E[MNU][MNU], ev[MNU];
-        bool finite = true;
-#pragma unroll
-        for (int i = 0; i < MNU; ++i) {
-            Qu[i] = i < nu ? sQu[i] : T(0);
-#pragma unroll
-            for (int j = 0; j < MNU; ++j) {
-                Quu[i][j] = (i < nu && j < nu) ? T(0.5) * (sQuu[i * MNU + j] + sQuu[j * MNU + i]) : T(0);
-                A[i][j] = Quu[i][j];
-                finite = finite && isfinite(Quu[i][j]);
+        if (work) {
+            for (int e = lane; e < nn; e += TEAM) {
+                const int i = e / nz, j = e - i * nz;
+                T s = a.L_zz[a.lLzz.at(b, t, e)];
+                for (int kk = 0; kk < nz; ++kk) s += Fz[kk * LD + i] * W[kk * LD + j];
+                V[i * LD + j] = s;
             }
         }
-        if (!finite) { ok = false; break; }                    // linalg.eig raises on NaN / Inf
-        // (A Cholesky test for "Q_uu is already positive definite, skip the eigen-decomposition" was tried and
-        // measured SLOWER on the rendezvous workload: 40.6 vs 30.5 ms.  With R = 0.1 I the symmetric problem's Q_uu is
-        // diagonal up to rounding and the Jacobi loop exits before its first rotation, while the extra factorisation
-        // costs square roots, divisions and registers.)
-        jacobi_eig(nu, A, E, ev);
+        // ---- small dense part ----
+        T Quu[MNU][MNU], Qu[MNU], kt[MNU], M[MNU][MNU];
+        if (HO) {
+            __syncthreads();                                   // every team's Q_uu / Q_u (and work flag) is parked
+            if (solver && s_alive && s_small[41] != T(0)) {    // s_small: Q_uu 0..15, Q_u 16..19, kt 20..23, M 24..39, ok 40, work 41
+                T sQ[MNU][MNU], sq[MNU], lot[MNU], hit[MNU], skt[MNU], sMm[MNU][MNU];
 #pragma unroll
-        for (int i = 0; i < MNU; ++i) {
-            if (ev[i] < T(0)) ev[i] = T(1e-12);                // ref: ilqr.py:633-634
-            ev[i] += reg;
-        }
-        T kt[MNU];
-        T M[MNU][MNU];                                         // K = -M Q_uz   (M = regularised inverse on the free dims)
-        if (!bounded) {
+                for (int i = 0; i < MNU; ++i) {
+                    sq[i] = i < nu ? s_small[16 + i] : T(0);
+                    const T ut = (bounded && i < nu) ? a.U[a.lU.at(sb, t, i)] : T(0);
+                    lot[i] = lo[i] - ut;
+                    hit[i] = hi[i] - ut;
 #pragma unroll
-                for (int i = 0; i < MNU; ++i)
+                    for (int j = 0; j < MNU; ++j)
+                        sQ[i][j] = (i < nu && j < nu) ? T(0.5) * (s_small[i * MNU + j] + s_small[j * MNU + i]) : T(0);
+                }
+                const bool sok = solve_small(nu, bounded, sQ, sq, s_reg, lot, hit, k_next, skt, sMm);
+#pragma unroll
+                for (int i = 0; i < MNU; ++i) {
+                    k_next[i] = skt[i];
+                    s_small[20 + i] = skt[i];
+#pragma unroll
+                    for (int j = 0; j < MNU; ++j) s_small[24 + i * MNU + j] = sMm[i][j];
+                }
+                s_small[40] = sok ? T(1) : T(0);
+            }
+            __syncthreads();
+            if (work) {
+#pragma unroll
+                for (int i = 0; i < MNU; ++i) {
+                    Qu[i] = i < nu ? sQu[i] : T(0);
+                    kt[i] = sKt[i];
 #pragma unroll
                     for (int j = 0; j < MNU; ++j) {
-                        T s = T(0);
-#pragma unroll
-                        for (int m = 0; m < MNU; ++m)
-                            if (m < nu) s += (E[i][m] / ev[m]) * E[j][m];
-                        M[i][j] = (i < nu && j < nu) ? s : T(0);
+                        Quu[i][j] = (i < nu && j < nu) ? T(0.5) * (sQuu[i * MNU + j] + sQuu[j * MNU + i]) : T(0);
+                        M[i][j] = sM[i * MNU + j];
                     }
+                }
+                ok = sOk[0] != T(0);
+            }
+        } else {
+            T lot[MNU], hit[MNU];
+#pragma unroll
+            for (int i = 0; i < MNU; ++i) {
+                Qu[i] = i < nu ? sQu[i] : T(0);
+                const T ut = (bounded && i < nu) ? a.U[a.lU.at(b, t, i)] : T(0);
+                lot[i] = lo[i] - ut;
+                hit[i] = hi[i] - ut;
+#pragma unroll
+                for (int j = 0; j < MNU; ++j)
+                    Quu[i][j] = (i < nu && j < nu) ? T(0.5) * (sQuu[i * MNU + j] + sQuu[j * MNU + i]) : T(0);
+            }
+            ok = solve_small(nu, bounded, Quu, Qu, reg, lot, hit, k_next, kt, M);
+#pragma unroll
+            for (int i = 0; i < MNU; ++i) k_next[i] = kt[i];
+            if (!ok) break;
+        }
+        const bool work2 = work && ok;
+        bool bad = false;
+        if (work2) {
+            for (int e = lane; e < nz * nu; e += TEAM) {
+                const int i = e / nz, c = e - i * nz;
+                T s = T(0);
+#pragma unroll
+                for (int j = 0; j < MNU; ++j)
+                    if (j < nu) s += M[i][j] * Quz[j * LD + c];      // M[i][j] indexed with a runtime i: small local array
+                s = -s;
+                Kt[i * LD + c] = s;
+                bad |= (s != s);
+            }
+        }
+        if (HO) {
+            if (work2) ok = !(__any_sync(nu_team_mask<TEAM>(), bad && !bounded));
+        } else {
+            ok = ok && !nu_team_any<TEAM>(bad && !bounded);    // the NaN test is on the unconstrained branch only
+            if (!ok) break;
+        }
+        if (HO && lane == 0) sOk[1] = (alive && ok) ? T(1) : T(0);   // work flag for the next hand-off
+        nu_team_sync<TEAM>();
+        if (alive && ok && work) {
+            for (int l = lane; l < nu; l += TEAM) {
+                T kv = T(0);
+#pragma unroll
+                for (int i = 0; i < MNU; ++i) if (i == l) kv = kt[i];
+                a.k[a.lk.at(b, t, l)] = kv;
+            }
+            for (int e = lane; e < nz * nu; e += TEAM) {
+                const int i = e / nz, c = e - i * nz;
+                a.K[a.lK.at(b, t, i * nz + c)] = Kt[i * LD + c];
+            }
+            // value update with the UN-regularised Q_uu (ref: ilqr.py:664-672)
+            T Quuk[MNU];                                           // Q_uu k
 #pragma unroll
             for (int i = 0; i < MNU; ++i) {
                 T s = T(0);
 #pragma unroll
-                for (int j = 0; j < MNU; ++j) s += M[i][j] * Qu[j];
-                kt[i] = -s;
-                if (kt[i] != kt[i]) ok = false;
+                for (int j = 0; j < MNU; ++j) s += Quu[i][j] * kt[j];
+                Quuk[i] = s;
             }
-        } else {
-            T Qreg[MNU][MNU], lot[MNU], hit[MNU], Uf[MNU][MNU];
+            for (int c = lane; c < nz; c += TEAM) {
+                T s = Qz[c];
 #pragma unroll
-            for (int i = 0; i < MNU; ++i) {
-                const T ut = i < nu ? a.U[a.lU.at(b, t, i)] : T(0);
-                lot[i] = lo[i] - ut;
-                hit[i] = hi[i] - ut;
-#pragma unroll
-                for (int j = 0; j < MNU; ++j) {
-                    T s = T(0);
-#pragma unroll
-                    for (int m = 0; m < MNU; ++m)
-                        if (m < nu) s += (E[i][m] * ev[m]) * E[j][m];
-                    Qreg[i][j] = s;
-                }
+                for (int i = 0; i < MNU; ++i)
+                    if (i < nu) s += Kt[i * LD + c] * (Qu[i] + Quuk[i]) + Quz[i * LD + c] * kt[i];
+                v[c] = s;
             }
-            unsigned free;
-            const int result = boxqp_n(nu, k_next, Qreg, Qu, lot, hit, kt, free, Uf);
-            if (result < 1) ok = false;                        // ref: ilqr.py:653-655
-            // M = (Q_uu_reg[free, free])^-1 scattered back, zero rows / columns for the clamped dims
-#pragma unroll
-            for (int j = 0; j < MNU; ++j) {
-                T r[MNU], x[MNU];
-#pragma unroll
-                for (int i = 0; i < MNU; ++i) r[i] = (i == j && ((free >> j) & 1u)) ? T(1) : T(0);
-                chol_solve(Uf, r, x);
-#pragma unroll
-                for (int i = 0; i < MNU; ++i) M[i][j] = (((free >> i) & 1u) && ((free >> j) & 1u)) ? x[i] : T(0);
-            }
-        }
-        bool bad = false;
-        for (int e = lane; e < nz * nu; e += TEAM) {
-            const int i = e / nz, c = e - i * nz;
-            T s = T(0);
-#pragma unroll
-            for (int j = 0; j < MNU; ++j)
-                if (j < nu) s += M[i][j] * Quz[j * LD + c];      // M[i][j] indexed with a runtime i: small local array
-            s = -s;
-            Kt[i * LD + c] = s;
-            bad |= (s != s);
-        }
-        ok = ok && !nu_team_any<TEAM>(bad && !bounded);        // the NaN test is on the unconstrained branch only
-        if (!ok) break;
-        nu_team_sync<TEAM>();
-#pragma unroll
-        for (int i = 0; i < MNU; ++i) k_next[i] = kt[i];
-        for (int l = lane; l < nu; l += TEAM) {
-            T kv = T(0);
-#pragma unroll
-            for (int i = 0; i < MNU; ++i) if (i == l) kv = kt[i];
-            a.k[a.lk.at(b, t, l)] = kv;
-        }
-        for (int e = lane; e < nz * nu; e += TEAM) {
-            const int i = e / nz, c = e - i * nz;
-            a.K[a.lK.at(b, t, i * nz + c)] = Kt[i * LD + c];
-        }
-        // value update with the UN-regularised Q_uu (ref: ilqr.py:664-672)
-        T Quuk[MNU];                                           // Q_uu k
-#pragma unroll
-        for (int i = 0; i < MNU; ++i) {
-            T s = T(0);
-#pragma unroll
-            for (int j = 0; j < MNU; ++j) s += Quu[i][j] * kt[j];
-            Quuk[i] = s;
-        }
-        for (int c = lane; c < nz; c += TEAM) {
-            T s = Qz[c];
-#pragma unroll
-            for (int i = 0; i < MNU; ++i)
-                if (i < nu) s += Kt[i * LD + c] * (Qu[i] + Quuk[i]) + Quz[i * LD + c] * kt[i];
-            v[c] = s;
         }
         nu_team_sync<TEAM>();                                  // V (= Q_zz) complete before it is symmetrised
-        for (int e = lane; e < nn; e += TEAM) {
-            const int i = e / nz, j = e - i * nz;
-            if (j < i) continue;
-            T val = T(0.5) * (V[i * LD + j] + V[j * LD + i]);
-            T kqk = T(0), cross = T(0);
+        if (alive && ok && work) {
+            for (int e = lane; e < nn; e += TEAM) {
+                const int i = e / nz, j = e - i * nz;
+                if (j < i) continue;
+                T val = T(0.5) * (V[i * LD + j] + V[j * LD + i]);
+                T kqk = T(0), cross = T(0);
 #pragma unroll
-            for (int p = 0; p < MNU; ++p) {
-                if (p >= nu) continue;
-                T qk = T(0);                                   // (Q_uu K)[p][j]
+                for (int p = 0; p < MNU; ++p) {
+                    if (p >= nu) continue;
+                    T qk = T(0);                                   // (Q_uu K)[p][j]
 #pragma unroll
-                for (int q = 0; q < MNU; ++q)
-                    if (q < nu) qk += Quu[p][q] * Kt[q * LD + j];
-                kqk += Kt[p * LD + i] * qk;
-                cross += Kt[p * LD + i] * Quz[p * LD + j] + Quz[p * LD + i] * Kt[p * LD + j];
+                    for (int q = 0; q < MNU; ++q)
+                        if (q < nu) qk += Quu[p][q] * Kt[q * LD + j];
+                    kqk += Kt[p * LD + i] * qk;
+                    cross += Kt[p * LD + i] * Quz[p * LD + j] + Quz[p * LD + i] * Kt[p * LD + j];
+                }
+                // 0.5 (X + X^T) of X = K^T Q_uu K + K^T Q_uz + Q_uz^T K: the first term is symmetric because the
+                // symmetrised Q_uu is, the other two are each other's transpose
+                val += kqk + cross;
+                V[i * LD + j] = val;
+                V[j * LD + i] = val;
             }
-            // 0.5 (X + X^T) of X = K^T Q_uu K + K^T Q_uz + Q_uz^T K: the first term is symmetric because the
-            // symmetrised Q_uu is, the other two are each other's transpose
-            val += kqk + cross;
-            V[i * LD + j] = val;
-            V[j * LD + i] = val;
         }
         nu_team_sync<TEAM>();
     }
-    if (lane == 0) a.status[b] = ok ? 0 : 1;
+    if (lane == 0 && alive) a.status[b] = ok ? 0 : 1;
 }
 
 template <class T, int TEAM, int NZC = 0, int NUC = 0>
@@ -495,7 +591,11 @@ static cudaError_t launch_nu_teams(const BackwardArgs<T>& a, size_t, cudaStream_
     int tpb = 128 / TEAM;                                   // teams (problems) per CTA
     while (tpb > 1 && per_team * tpb > 200 * 1024) tpb >>= 1;
     const size_t smem = per_team * tpb;
-    auto kern = backward_nu_kernel<T, TEAM, NZC, NUC>;
+    // PDDP_BACKWARD_NU_HANDOFF=0: every team solves its own small dense part (A/B measurements)
+    static int handoff = -1;
+    if (handoff < 0) { const char* e = getenv("PDDP_BACKWARD_NU_HANDOFF"); handoff = (e && e[0] == '0') ? 0 : 1; }
+    auto kern = backward_nu_kernel<T, TEAM, NZC, NUC, false>;
+    if constexpr (TEAM < 32) { if (handoff) kern = backward_nu_kernel<T, TEAM, NZC, NUC, true>; }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(a.B + tpb - 1) / tpb, tpb * TEAM, smem, s>>>(a);

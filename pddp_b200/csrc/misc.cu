@@ -83,9 +83,46 @@ __global__ void accept_copy_kernel(const AcceptArgs<T> a, const int32_t* accepte
     }
 }
 
+// BATCH_INNER: Z, U and K are flat [row][B] arrays (row = t * E + e), so the copy is three masked row copies.  A thread
+// owns ONE problem (a warp's accesses are one coalesced line whatever the acceptance mask looks like) and walks the rows
+// with a stride of gridDim.y, 8 rows in flight: no index arithmetic per element (the generic kernel's 64-bit divisions
+// made it instruction bound: 2.0 TB/s at 2^20 pendulums).
+template <class T>
+__global__ void __launch_bounds__(256) accept_copy_inner_kernel(const AcceptArgs<T> a, const int32_t* accepted) {
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= a.B || !accepted[b]) return;
+    const int64_t rowsZ = (int64_t)(a.N + 1) * a.nz, rowsU = (int64_t)a.N * a.nu;
+    const int64_t rowsK = a.K_nominal ? (int64_t)a.N * a.nu * a.nz : 0;
+    constexpr int UR = 8;
+    auto copy_rows = [&](const T* src, T* dst, int64_t nrows) {
+        for (int64_t r0 = (int64_t)blockIdx.y * UR; r0 < nrows; r0 += (int64_t)gridDim.y * UR) {
+            T tmp[UR];
+#pragma unroll
+            for (int u = 0; u < UR; ++u)
+                if (r0 + u < nrows) tmp[u] = __ldg(src + (r0 + u) * a.B + b);
+#pragma unroll
+            for (int u = 0; u < UR; ++u)
+                if (r0 + u < nrows) dst[(r0 + u) * a.B + b] = tmp[u];
+        }
+    };
+    copy_rows(a.Z_new, a.Z, rowsZ);
+    copy_rows(a.U_new, a.U, rowsU);
+    if (rowsK) copy_rows(a.K, a.K_nominal, rowsK);
+}
+
 template <class T>
 cudaError_t accept_update(const AcceptArgs<T>& a, int32_t* accepted_scratch, cudaStream_t s) {
     accept_state_kernel<T><<<(a.B + 127) / 128, 128, 0, s>>>(a, accepted_scratch);
+    if (a.lZ.sb == 1) {                                     // BATCH_INNER
+        const int64_t rows = (int64_t)(a.N + 1) * a.nz + (int64_t)a.N * a.nu + (a.K_nominal ? (int64_t)a.N * a.nu * a.nz : 0);
+        const unsigned gx = (unsigned)(((int64_t)a.B + 255) / 256);
+        int64_t gy = (148 * 16 + gx - 1) / gx;              // ~16 CTAs per SM in flight, each thread several rows
+        if (gy > (rows + 7) / 8) gy = (rows + 7) / 8;
+        if (gy > 65535) gy = 65535;
+        if (gy < 1) gy = 1;
+        accept_copy_inner_kernel<T><<<dim3(gx, (unsigned)gy), 256, 0, s>>>(a, accepted_scratch);
+        return cudaGetLastError();
+    }
     const int64_t total = ((int64_t)(a.N + 1) * a.nz + (int64_t)a.N * a.nu +
                            (a.K_nominal ? (int64_t)a.N * a.nu * a.nz : 0)) * a.B;
     int grid = (int)((total + 255) / 256);

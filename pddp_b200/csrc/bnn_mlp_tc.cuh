@@ -896,8 +896,16 @@ bnn_mlp_tc_kernel(const BnnMlpArgs<float> a, const Images im, int S, int tiles_p
                                 sts128(A1 + ((c ^ row_sw) << 4), a0[4 * c], a0[4 * c + 1], a0[4 * c + 2], a0[4 * c + 3]);
                                 sts128(A1 + (((2 + c) ^ row_sw) << 4), a1[4 * c], a1[4 * c + 1], a1[4 * c + 2], a1[4 * c + 3]);
                             }
+#ifdef PDDP_EXP_FENCE_MERGE           // one proxy fence per chunk: both K-blocks are published after the second one's stores
+                            if (h == nk - 1) {
+                                fence_async_smem();
+                                if (nk == 2) mbar_arrive(&a1_full[t * NS + (slot == 0 ? NS - 1 : slot - 1)]);
+                                mbar_arrive(&a1_full[t * NS + slot]);
+                            }
+#else
                             fence_async_smem();
                             mbar_arrive(&a1_full[t * NS + slot]);
+#endif
                             if (++slot == NS) { slot = 0; sph ^= 1; }
                         }
                     }

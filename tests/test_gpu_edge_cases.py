@@ -54,7 +54,7 @@ def _small_bnn(O, P, H, seed):
 
 def _check_against_oracle(O, solver, odyn, ocost, enc, z0, U, alphas, reg, tol=1e-6):
     B = z0.shape[0]
-    solver.set_problem(z0.cuda(), U.cuda(), alphas=alphas)
+    solver.set_problem(z0.to(solver.dtype).cuda(), U.to(solver.dtype).cuda(), alphas=alphas.to(solver.dtype))
     solver.mu.fill_(reg)
     solver.linearize(); solver.backward(); solver.rollout()
     torch.cuda.synchronize()
@@ -66,12 +66,16 @@ def _check_against_oracle(O, solver, odyn, ocost, enc, z0, U, alphas, reg, tol=1
         Zb, Ub = O.rollout(odyn, lin[0], U[b], k, K, alphas, enc)
         J = O.trajectory_cost(ocost, Zb, Ub, enc)
         pairs = [(solver.matrices(n).cpu()[b], w) for n, w in zip("Z F_z F_u L L_z L_u L_zz L_uz L_uu".split(), lin)]
-        amin = int(J.argmin())
+        # the kernel's winner must be the oracle's minimum -- up to the tolerance: in fp32 two step sizes whose costs
+        # agree to rounding may swap
+        amin = int(solver.amin.cpu()[b])
+        assert float(J[amin]) <= float(J.min()) + tol * max(1.0, float(J.abs().max()))
+        if tol <= 1e-6:
+            assert amin == int(J.argmin())
         pairs += [(solver.matrices("k").cpu()[b], k), (solver.matrices("K").cpu()[b], K), (solver.J_all.cpu()[b], J),
                   (solver.view("Z_new").cpu()[b], Zb[:, amin]), (solver.view("U_new").cpu()[b], Ub[:, amin])]
-        assert int(solver.amin.cpu()[b]) == amin
         for got, want in pairs:
-            err = (got.reshape(want.shape) - want).abs().max().item() / max(1.0, want.abs().max().item())
+            err = (got.double().reshape(want.shape) - want).abs().max().item() / max(1.0, want.abs().max().item())
             worst = max(worst, err)
     assert worst < tol, worst
 
@@ -107,6 +111,35 @@ def test_degenerate_shapes_bnn(B, N, A, P):
                       QRCostConstants(ocost.Q, ocost.R, ocost.Q_term, ocost.x_goal), O.DEFAULT, B, N, dtype=F64,
                       max_alphas=max(A, 1))
     _check_against_oracle(O, s, odyn, ocost, O.DEFAULT, z0, U, O.fit_alphas(F64, A), 1.0)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-6), (torch.float32, 1e-3)])
+@pytest.mark.parametrize("B,N,A,P", [(3, 2, 5, 7), (1, 3, 3, 5)])
+def test_pendulum_bnn_odd_particle_and_pair_counts(B, N, A, P, dtype, tol):
+    """Pendulum BNN (D = 2): a (problem, alpha) pair's particle block is 8 P bytes in fp32, so with an odd P and an odd
+    number of pairs the roll-step kernel's bulk copy is rounded up to 16 bytes (it reads into the workspace padding), the
+    staged rows are 8-byte rows, and the last CTA is ragged.  Against the CPU oracle on the same inputs."""
+    import pddp_oracle as O
+    from pddp_b200 import _lib
+    from pddp_b200.solver import BatchedSolver, BNNDynamics, QRCostConstants
+    ocost = _pendulum_cost(O)
+    g = torch.Generator().manual_seed(17 * P + A)
+    D, H = 2, 32
+    W = [torch.randn(H, 4, generator=g, dtype=F64) * 0.5, torch.randn(H, H, generator=g, dtype=F64) * 0.25,
+         torch.randn(2 * D, H, generator=g, dtype=F64) * 0.02]
+    b = [0.1 * torch.randn(H, generator=g, dtype=F64), 0.1 * torch.randn(H, generator=g, dtype=F64),
+         0.01 * torch.randn(2 * D, generator=g, dtype=F64)]
+    masks = [torch.rand(P, H, generator=g, dtype=F64), torch.rand(P, H, generator=g, dtype=F64)]
+    eps = torch.randn(P, D, generator=g, dtype=F64)
+    eps0 = (eps - eps.mean(0)) / eps.std(0)
+    odyn = O.BNNSpec(list(zip(W, b)), masks, eps0, D, 1, (0,), (1,))
+    mean = 1e-2 * torch.randn(B, D, generator=g, dtype=F64)
+    z0 = torch.stack([O.encode(m, V=1e-2 * torch.ones(D, dtype=F64), enc=O.DEFAULT) for m in mean])
+    U = 0.1 * torch.randn(B, N, 1, generator=g, dtype=F64)
+    s = BatchedSolver(BNNDynamics(_lib.GEO_PENDULUM, W, b, masks, eps0),
+                      QRCostConstants(ocost.Q, ocost.R, ocost.Q_term, ocost.x_goal), O.DEFAULT, B, N, dtype=dtype,
+                      max_alphas=A)
+    _check_against_oracle(O, s, odyn, ocost, O.DEFAULT, z0, U, O.fit_alphas(F64, A), 1.0, tol=tol)
 
 
 def test_inactive_problems_are_untouched():

@@ -362,15 +362,17 @@ __global__ void __launch_bounds__(128, (sizeof(T) == 4 && WPP == 1 && Geo<GEO>::
     }
 }
 
-// clamp the nominal controls of step t into ucur[b] (and park them for the cost pass)
+// clamp the nominal controls of EVERY step into uall[t][b] (the MLP of step t reads row t) and park them in the
+// problem layout for the cost pass -- one launch instead of one per time step (they do not depend on the state)
 template <class T>
-__global__ void bnn_lin_control_kernel(int B, int t, const T* U, Layout lU, const T* u_min, const T* u_max,
-                                       T* ucur, T* U_clamped) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+__global__ void bnn_lin_control_kernel(int B, int N, const T* U, Layout lU, const T* u_min, const T* u_max,
+                                       T* uall, T* U_clamped) {
+    const long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (id >= (long long)B * N) return;
+    const int t = (int)(id / B), b = (int)(id - (long long)t * B);
     T u = U[lU.at(b, t, 0)];
     if (u_min && u_max) u = clampv(u, u_min[0], u_max[0]);
-    ucur[b] = u;
+    uall[id] = u;
     U_clamped[lU.at(b, t, 0)] = u;
 }
 
@@ -677,11 +679,13 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
     CK(cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
 
     BnnMlpArgs<T> a;
-    a.net = net; a.u = w.ucur; a.Jp = w.Jp; a.total = total;
+    a.net = net; a.Jp = w.Jp; a.total = total;
     T *cur = w.Xa, *nxt = w.Xb;
+    // (w.Uall is [B * N] in this pass: the all-alpha control buffer of the rollout pass, free here)
+    bnn_lin_control_kernel<T><<<(unsigned)(((long long)B * N + 255) / 256), 256, 0, c.st>>>(
+        B, N, (const T*)c.U, lU, (const T*)c.u_min, (const T*)c.u_max, w.Uall, (T*)c.L_u);
     for (int t = 0; t < N; ++t) {
-        bnn_lin_control_kernel<T><<<(B + 127) / 128, 128, 0, c.st>>>(B, t, (const T*)c.U, lU, (const T*)c.u_min,
-                                                                  (const T*)c.u_max, w.ucur, (T*)c.L_u);
+        a.u = w.Uall + (size_t)t * B;
         if (mode != PDDP_BNN_INPUT_INFER && t > 0)
             bnn_init_particles_kernel<T, GEO, ENC><<<igrid, 128, 0, c.st>>>(Z, lZ, t, 1, 1, B, P, eps_of(t), c.active, 1,
                                                                             nullptr, cur, c.status);
@@ -707,7 +711,7 @@ static cudaError_t linearize_bnn_impl(const BnnCall& c) {
     cd.lZ = lZ; cd.lU = lU; cd.lL = make_layout(ly, B, N + 1, 1); cd.lLz = make_layout(ly, B, N + 1, nz);
     cd.lLu = make_layout(ly, B, N, nu); cd.lLzz = make_layout(ly, B, N + 1, nz * nz);
     cd.lLuz = make_layout(ly, B, N, nu * nz); cd.lLuu = make_layout(ly, B, N, nu * nu);
-    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 10 : 5) + 2 + 3LL * N + 2 + (s->enc == PDDP_ENC_FULL_COVARIANCE_MATRIX ? 1 : 0)
+    note_launches((use_tensor_cores<T>(c.n->H0, c.n->H1) ? 10 : 5) + 3 + 2LL * N + 2 + (s->enc == PDDP_ENC_FULL_COVARIANCE_MATRIX ? 1 : 0)
                   + (mode != PDDP_BNN_INPUT_INFER ? N - 1 : 0));
     prof_begin(PROF_COST, c.st);
     cudaError_t ce = cost_derivatives<T>(s->geo, s->enc, cd, c.st);

@@ -398,7 +398,8 @@ struct RollStepArgs {
 // first 256 / LPP threads, one per pair, do the encode (Cholesky), control law and moment-matched cost.
 // (History: one thread per pair issued 2 x P strided 4-byte loads per sector and ran at 9 % issue utilisation; 8 lanes
 // per pair reading global memory directly spent the launch in 2 x P / LPP dependent round trips to L2: 28 us.)
-template <class T, int GEO, int ENC, int LPP>
+// STAGE = false: the particles of 32 pairs do not fit shared memory (very large P): phase A reads them from global memory.
+template <class T, int GEO, int ENC, int LPP, bool STAGE = true>
 __global__ void __launch_bounds__(256) bnn_roll_step_kernel(const RollStepArgs<T> a) {
     typedef Geo<GEO> G;
     constexpr int D = G::D, NZ = enc_size(D, ENC), NT = D * (D + 1) / 2, PPC = 256 / LPP;
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(256) bnn_roll_step_kernel(const RollStepArgs<T
     const long long S = (long long)a.B * a.A;
     const int P = a.P, t1 = a.t + 1;
     const long long s0 = (long long)blockIdx.x * PPC;
-    if (a.t >= 0) {
+    if (STAGE && a.t >= 0) {
         if (tid == 0) bulk_mbar_init(&s_bar, 1);
         __syncthreads();
         if (tid == 0) {
@@ -436,10 +437,10 @@ __global__ void __launch_bounds__(256) bnn_roll_step_kernel(const RollStepArgs<T
         if (run && a.t >= 0) Jprev = a.J[sB];
     }
     if (a.t >= 0) {
-        bulk_mbar_wait(&s_bar, 0);
+        if (STAGE) bulk_mbar_wait(&s_bar, 0);
         const int pr = tid / LPP, sub = tid % LPP;
         const bool live = s0 + pr < S;
-        const T* X = s_X + (size_t)pr * P * D;
+        const T* X = STAGE ? s_X + (size_t)pr * P * D : a.Xn + (size_t)(live ? s0 + pr : 0) * P * D;
         T M[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) M[d] = T(0);
@@ -758,9 +759,10 @@ static cudaError_t rollout_bnn_impl(const BnnRollCall& c) {
     const size_t pair_bytes = (size_t)P * D * sizeof(T);
     const bool lpp4 = (S + 31) / 32 > (long long)num_sms() * 4 && 64 * pair_bytes <= 100 * 1024;
     const unsigned rgrid = (unsigned)(lpp4 ? (S + 63) / 64 : (S + 31) / 32);
-    const size_t rsmem = (lpp4 ? 64 : 32) * pair_bytes + 16;
-    if (rsmem > 200 * 1024) return cudaErrorInvalidValue;       // (particles of 32 pairs must fit shared memory)
-    auto roll_step = lpp4 ? bnn_roll_step_kernel<T, GEO, ENC, 4> : bnn_roll_step_kernel<T, GEO, ENC, 8>;
+    const bool stage = 32 * pair_bytes + 16 <= 200 * 1024;       // else: particles straight from global memory
+    const size_t rsmem = stage ? (lpp4 ? 64 : 32) * pair_bytes + 16 : 0;
+    auto roll_step = !stage ? bnn_roll_step_kernel<T, GEO, ENC, 8, false>
+                   : lpp4 ? bnn_roll_step_kernel<T, GEO, ENC, 4> : bnn_roll_step_kernel<T, GEO, ENC, 8>;
     CK(cudaFuncSetAttribute(roll_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
     r.t = -1; r.Xn = w.Xa;
     roll_step<<<rgrid, 256, rsmem, c.st>>>(r);

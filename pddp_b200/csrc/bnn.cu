@@ -68,7 +68,7 @@ __global__ void bnn_init_particles_kernel(const T* z, Layout lz, int t, int zdiv
 }
 
 // ------------------------------------------------------------------------------------------
-// linearise: moment matching + Jacobian of one step, one warp per problem
+// linearise: moment matching + Jacobian of one step, a team of 1 or 2 warps per problem
 // ------------------------------------------------------------------------------------------
 // shared-memory elements of ONE problem in bnn_moment_lin_kernel (arrays padded to 16 bytes)
 template <int D, int WPP>
@@ -377,7 +377,7 @@ __global__ void bnn_lin_control_kernel(int B, int N, const T* U, Layout lU, cons
 }
 
 // ------------------------------------------------------------------------------------------
-// rollout: one warp per (problem, alpha)
+// rollout: 8 or 4 lanes per (problem, alpha) pair, then one finishing thread per pair
 // ------------------------------------------------------------------------------------------
 template <class T>
 struct RollStepArgs {

@@ -163,17 +163,28 @@ __device__ __forceinline__ T roll_one(const RollKnownArgs<T>& a, int b, T alpha,
 #pragma unroll
     for (int e = 0; e < NZ; ++e) z[e] = a.Z[a.lZ.at(b, 0, e)];
     T J = T(0);
+    // running pointers into the step records (the loop is bound by instruction issue: the 64-bit index arithmetic of
+    // six Layout::at() calls per step was a quarter of it)
+    const T* pZ = a.Z + a.lZ.at(b, 0, 0);
+    const T* pK = a.K + a.lK.at(b, 0, 0);
+    const T* pk = a.k + a.lk.at(b, 0, 0);
+    const T* pU = a.U + a.lU.at(b, 0, 0);
+    T* pZn = STORE ? a.Z_new + a.lZ.at(b, 0, 0) : nullptr;
+    T* pUn = STORE ? a.U_new + a.lU.at(b, 0, 0) : nullptr;
+    const int64_t seZ = a.lZ.se, seK = a.lK.se;
     for (int t = 0; t < a.N; ++t) {
-        T du = alpha * a.k[a.lk.at(b, t, 0)];
+        T du = alpha * pk[0];
 #pragma unroll
-        for (int e = 0; e < NZ; ++e) du += (z[e] - a.Z[a.lZ.at(b, t, e)]) * a.K[a.lK.at(b, t, e)];
-        T u = a.U[a.lU.at(b, t, 0)] + du;
+        for (int e = 0; e < NZ; ++e) du += (z[e] - pZ[e * seZ]) * pK[e * seK];
+        T u = pU[0] + du;
         if (bounded) u = clampv(u, lo, hi);
         if (STORE) {
 #pragma unroll
-            for (int e = 0; e < NZ; ++e) a.Z_new[a.lZ.at(b, t, e)] = z[e];
-            a.U_new[a.lU.at(b, t, 0)] = u;
+            for (int e = 0; e < NZ; ++e) pZn[e * seZ] = z[e];
+            pUn[0] = u;
+            pZn += a.lZ.st; pUn += a.lU.st;
         }
+        pZ += a.lZ.st; pK += a.lK.st; pk += a.lk.st; pU += a.lU.st;
         StateTrig<GEO, T> tr;                               // shared by the cost and the dynamics of this step
         state_trig<GEO, T>(z, tr);
         if (!STORE) {
@@ -189,7 +200,7 @@ __device__ __forceinline__ T roll_one(const RollKnownArgs<T>& a, int b, T alpha,
     }
     if (STORE) {
 #pragma unroll
-        for (int e = 0; e < NZ; ++e) a.Z_new[a.lZ.at(b, a.N, e)] = z[e];
+        for (int e = 0; e < NZ; ++e) pZn[e * seZ] = z[e];
     } else {
         J += cost_state<GEO, ENC, T, T>(a.cost, z, true);
     }

@@ -297,24 +297,34 @@ __device__ __forceinline__ T lq_roll_one(const RollKnownArgs<T>& a, int b, T alp
     T z[NZ], zn[NZ];
     for (int e = 0; e < NZ; ++e) z[e] = a.Z[a.lZ.at(b, 0, e)];
     T J = T(0);
+    // running pointers into the step records (48 loads per step: no Layout::at() index arithmetic in the loop)
+    const T* pZ = a.Z + a.lZ.at(b, 0, 0);
+    const T* pK = a.K + a.lK.at(b, 0, 0);
+    const T* pk = a.k + a.lk.at(b, 0, 0);
+    const T* pU = a.U + a.lU.at(b, 0, 0);
+    T* pZn = STORE ? a.Z_new + a.lZ.at(b, 0, 0) : nullptr;
+    T* pUn = STORE ? a.U_new + a.lU.at(b, 0, 0) : nullptr;
+    const int64_t seZ = a.lZ.se, seK = a.lK.se, sek = a.lk.se, seU = a.lU.se;
     for (int t = 0; t < a.N; ++t) {
         T u[NU];
 #pragma unroll
-        for (int i = 0; i < NU; ++i) u[i] = alpha * a.k[a.lk.at(b, t, i)];
+        for (int i = 0; i < NU; ++i) u[i] = alpha * pk[i * sek];
         for (int e = 0; e < NZ; ++e) {
-            const T dz = z[e] - a.Z[a.lZ.at(b, t, e)];
+            const T dz = z[e] - pZ[e * seZ];
 #pragma unroll
-            for (int i = 0; i < NU; ++i) u[i] += dz * a.K[a.lK.at(b, t, i * NZ + e)];
+            for (int i = 0; i < NU; ++i) u[i] += dz * pK[(i * NZ + e) * seK];
         }
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
-            u[i] += a.U[a.lU.at(b, t, i)];
+            u[i] += pU[i * seU];
             if (bounded) u[i] = clampv(u[i], a.u_min[i], a.u_max[i]);
         }
+        pZ += a.lZ.st; pK += a.lK.st; pk += a.lk.st; pU += a.lU.st;
         if (STORE) {
-            for (int e = 0; e < NZ; ++e) a.Z_new[a.lZ.at(b, t, e)] = z[e];
+            for (int e = 0; e < NZ; ++e) pZn[e * seZ] = z[e];
 #pragma unroll
-            for (int i = 0; i < NU; ++i) a.U_new[a.lU.at(b, t, i)] = u[i];
+            for (int i = 0; i < NU; ++i) pUn[i * seU] = u[i];
+            pZn += a.lZ.st; pUn += a.lU.st;
         } else {
             J += rdv_cost_state<ENC, T>(a.cost, z, false) + rdv_cost_action(a.cost, u);
         }
@@ -324,7 +334,7 @@ __device__ __forceinline__ T lq_roll_one(const RollKnownArgs<T>& a, int b, T alp
         for (int e = 0; e < NZ; ++e) z[e] = zn[e];
     }
     if (STORE) {
-        for (int e = 0; e < NZ; ++e) a.Z_new[a.lZ.at(b, a.N, e)] = z[e];
+        for (int e = 0; e < NZ; ++e) pZn[e * seZ] = z[e];
     } else {
         J += rdv_cost_state<ENC, T>(a.cost, z, true);
     }
